@@ -1,0 +1,273 @@
+"""
+tests/golden/make_golden.py -- regenerates the golden vectors under tests/golden/.
+
+Runs ONLY in the build container: it imports the unmodified reference modules from
+/root/reference/src (read-only) and records, with fixed seeds, what the reference's own
+PyTorch-autograd implementation returns on the hot path.  The GPU box never runs this; it reads
+the committed .npz files.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Every fixture stores the model's state_dict (prefix "sd/") so no checkpoint has to travel.
+Reference entry points exercised (paths under /root/reference):
+  src/pHNN.py:52-100, src/pHNN_canonical.py:172-273, src/integrators.py:13-258,
+  src/mpc_controller.py:75-209, src/mpc_controller_canonical.py:91-273.
+"""
+import os
+import sys
+import tempfile
+
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+
+import numpy as np
+import torch
+import yaml
+
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(REF, "src"))
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+CFG = os.path.join(REPO, "configs")
+
+from pHNN import pHNN  # noqa: E402  (reference)
+from pHNN_canonical import pHNN_Canonical  # noqa: E402
+from integrators import rollout_trajectory, rollout_trajectory_differentiable  # noqa: E402
+from mpc_controller import MPCController  # noqa: E402
+from mpc_controller_canonical import create_mpc_controller  # noqa: E402
+
+torch.set_num_threads(1)
+
+
+def sd_np(model):
+    return {"sd/" + k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def wide_cfg(hidden):
+    cfg = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    cfg["model"]["H_mlp"]["hidden_sizes"] = [hidden, hidden]
+    cfg["model"]["R_mlp"]["hidden_sizes"] = [hidden]
+    f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+    yaml.safe_dump(cfg, f)
+    f.close()
+    return f.name
+
+
+def fwd_and_vjp(model, x, u, v):
+    """model forward, and (d dx/d x)^T v, (d dx/d u)^T v by autograd."""
+    x = x.clone().requires_grad_(True)
+    u = u.clone().requires_grad_(True)
+    out = model(x, u)
+    dx, H = out[0], out[1]
+    gx, gu = torch.autograd.grad((dx * v).sum(), [x, u])
+    return dx.detach(), H.detach(), gx, gu
+
+
+def batched_cost(traj, Uc, Q, R, xt):
+    e = traj - xt
+    sc = torch.einsum("bti,ij,btj->b", e, Q, e)
+    cc = torch.einsum("bti,ij,btj->b", Uc, R, Uc)
+    return sc + cc
+
+
+def composition_solve(model, x0, U0, dt, integrator, Q, R, xt, umin, umax, lr, iters, mode):
+    """Batched composition of reference pieces: clamp ->
+    rollout_trajectory_differentiable -> quadratic cost -> backward -> torch.optim.Adam."""
+    U = U0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([U], lr=lr)
+    hist, grads = [], []
+    best = torch.full((x0.shape[0],), float("inf"))
+    Ubest = torch.clamp(U0, umin, umax).clone()
+    for _ in range(iters):
+        opt.zero_grad()
+        Uc = torch.clamp(U, umin, umax)
+        traj = rollout_trajectory_differentiable(model, x0.clone().requires_grad_(True), Uc, dt, integrator)
+        cost = batched_cost(traj, Uc, Q, R, xt)
+        cost.sum().backward()
+        grads.append(U.grad.detach().clone())
+        hist.append(cost.detach().clone())
+        better = cost.detach() < best
+        best = torch.where(better, cost.detach(), best)
+        Ubest[better] = Uc.detach()[better]
+        opt.step()
+    Ulast = torch.clamp(U.detach(), umin, umax)
+    return dict(U_last=Ulast.numpy(), U_best=Ubest.numpy(), best=best.numpy(), hist=torch.stack(hist).numpy(),
+                grad0=grads[0].numpy(), grad_last=grads[-1].numpy())
+
+
+def gen_pendulum():
+    model = pHNN(os.path.join(CFG, "pendulum_phnn.yaml"))
+    model.load_state_dict(torch.load(os.path.join(REF, "pendulum_pHNN_weights.pth"), map_location="cpu"))
+    model.eval()
+    out = sd_np(model)
+    # Appendix C anchors
+    x = torch.tensor([[1.0, 0.5], [-2.0, 0.25]])
+    u = torch.tensor([[0.3], [-1.0]])
+    v = torch.tensor([[0.7, -0.2], [0.1, 1.3]])
+    dx, H, gx, gu = fwd_and_vjp(model, x, u, v)
+    out.update(anchor_x=x.numpy(), anchor_u=u.numpy(), anchor_v=v.numpy(), anchor_dx=dx.numpy(), anchor_H=H.numpy(),
+               anchor_gx=gx.numpy(), anchor_gu=gu.numpy())
+    U10 = u[:, None, :].repeat(1, 10, 1)
+    for integ in ("rk4", "euler"):
+        tr, en = rollout_trajectory_differentiable(model, x.clone().requires_grad_(True), U10, 0.05, integ, True)
+        out["anchor_traj_" + integ] = tr.detach().numpy()
+        out["anchor_en_" + integ] = en.detach().numpy()
+        tr2, en2 = rollout_trajectory(model, x.clone().requires_grad_(True), U10, 0.05, integ)
+        out["anchor_traj2_" + integ] = tr2.detach().numpy()
+        out["anchor_en2_" + integ] = en2.detach().numpy()
+    Ug = U10.clone().requires_grad_(True)
+    tr = rollout_trajectory_differentiable(model, x.clone().requires_grad_(True), Ug, 0.05, "rk4")
+    Jv = (tr ** 2).sum()
+    Jv.backward()
+    out.update(anchor_J=np.float32(Jv.item()), anchor_dJdU=Ug.grad.numpy())
+    # config-2 style inputs, small
+    g = torch.Generator().manual_seed(1)
+    B, T = 64, 100
+    th = (torch.rand(B, generator=g) * 2 - 1) * np.pi
+    om = torch.rand(B, generator=g) * 2 - 1
+    x0 = torch.stack([th, om], 1)
+    U = (torch.rand(B, T, 1, generator=g) * 4 - 2)
+    for integ in ("rk4", "euler"):
+        tr, en = rollout_trajectory_differentiable(model, x0.clone().requires_grad_(True), U, 0.05, integ, True)
+        out["cfg2_traj_" + integ] = tr.detach().numpy()
+        out["cfg2_en_" + integ] = en.detach().numpy()
+    out.update(cfg2_x0=x0.numpy(), cfg2_U=U.numpy())
+    # random forward / vjp points
+    xr = torch.randn(32, 2, generator=g) * 2
+    ur = torch.randn(32, 1, generator=g)
+    vr = torch.randn(32, 2, generator=g)
+    dx, H, gx, gu = fwd_and_vjp(model, xr, ur, vr)
+    out.update(rand_x=xr.numpy(), rand_u=ur.numpy(), rand_v=vr.numpy(), rand_dx=dx.numpy(), rand_H=H.numpy(),
+               rand_gx=gx.numpy(), rand_gu=gu.numpy())
+    # quadratic-cost gradient through the learned-G model (euler + rk4)
+    Q = torch.diag(torch.tensor([5.0, 1.0]))
+    R = torch.tensor([[0.1]])
+    xt = torch.tensor([0.5, 0.0])
+    res = {}
+    for integ in ("euler", "rk4"):
+        res = composition_solve(model, x0[:8], U[:8, :15] * 1.2, 0.05, integ, Q, R, xt, -2.0, 2.0, 0.05, 6, "last")
+        for k, val in res.items():
+            out["mpc_%s_%s" % (integ, k)] = val
+    out.update(mpc_x0=x0[:8].numpy(), mpc_U0=(U[:8, :15] * 1.2).numpy(), mpc_Q=Q.numpy(), mpc_R=R.numpy(),
+               mpc_xt=xt.numpy(), mpc_bounds=np.array([-2.0, 2.0], np.float32), mpc_lr=np.float32(0.05),
+               mpc_dt=np.float32(0.05))
+    np.savez(os.path.join(HERE, "pendulum.npz"), **out)
+    print("pendulum: anchor dx", dx[:1].numpy() if False else out["anchor_dx"], "J", out["anchor_J"])
+
+
+def cartpole_points(g, B):
+    x = (torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])
+    u = (torch.rand(B, 1, generator=g) * 2 - 1) * 10
+    v = torch.randn(B, 4, generator=g)
+    return x, u, v
+
+
+def gen_cartpole(hidden, seed, name):
+    cfg_path = os.path.join(CFG, "cartpole_phnn.yaml") if hidden == 128 else wide_cfg(hidden)
+    torch.manual_seed(seed)
+    model = pHNN(cfg_path)
+    model.eval()
+    cfg = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    mpc = cfg["mpc"]
+    out = sd_np(model)
+    g = torch.Generator().manual_seed(7)
+    x, u, v = cartpole_points(g, 32)
+    dx, H, gx, gu = fwd_and_vjp(model, x, u, v)
+    out.update(rand_x=x.numpy(), rand_u=u.numpy(), rand_v=v.numpy(), rand_dx=dx.numpy(), rand_H=H.numpy(),
+               rand_gx=gx.numpy(), rand_gu=gu.numpy())
+    # wide-range states as in data/cartpole_training_data.pt
+    xw = torch.randn(16, 4, generator=g) * torch.tensor([5.0, 3.0, 4.0, 4.0])
+    dxw, Hw, gxw, guw = fwd_and_vjp(model, xw, u[:16], v[:16])
+    out.update(wide_x=xw.numpy(), wide_dx=dxw.numpy(), wide_H=Hw.numpy(), wide_gx=gxw.numpy())
+    Q = torch.diag(torch.tensor(mpc["Q_diag"]))
+    R = torch.tensor([[mpc["R_diag"][0]]])
+    xt = torch.tensor(mpc["x_target"])
+    dt = cfg["cartpole"]["dt"]
+    B, Hh, iters = 8, 12, 5
+    x0 = x[:B]
+    U0 = (torch.rand(B, Hh, 1, generator=g) * 2 - 1) * 18.0       # some entries beyond the +-15 bounds
+    out.update(mpc_x0=x0.numpy(), mpc_U0=U0.numpy(), mpc_Q=Q.numpy(), mpc_R=R.numpy(), mpc_xt=xt.numpy(),
+               mpc_bounds=np.array([mpc["u_min"], mpc["u_max"]], np.float32), mpc_lr=np.float32(mpc["learning_rate"]),
+               mpc_dt=np.float32(dt))
+    for integ in ("euler", "rk4"):
+        res = composition_solve(model, x0, U0, dt, integ, Q, R, xt, mpc["u_min"], mpc["u_max"], mpc["learning_rate"],
+                                iters, "last")
+        for k, val in res.items():
+            out["mpc_%s_%s" % (integ, k)] = val
+        tr = rollout_trajectory_differentiable(model, x0.clone().requires_grad_(True),
+                                               torch.clamp(U0, mpc["u_min"], mpc["u_max"]), dt, integ)
+        out["mpc_%s_traj0" % integ] = tr.detach().numpy()
+    if hidden == 128:
+        # the real controller, single instance, YAML parameters (config 1)
+        ctrl = MPCController(model, mpc["horizon"], dt, mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"], mpc["u_min"],
+                             mpc["u_max"], optimizer_type="Adam", lr=mpc["learning_rate"],
+                             max_iterations=mpc["optimizer_steps"])
+        xs = np.array([[0.0, 0.1, 0.0, 0.0], [0.3, -0.12, 0.2, -0.4], [-0.5, 0.2, -0.3, 0.6]], np.float64)
+        us = [ctrl.compute_control(s) for s in xs]
+        out.update(ctrl_x=xs, ctrl_u=np.stack(us))
+        # with soft state bounds (the optional barrier term, src/mpc_controller.py:96-107)
+        ctrl_b = MPCController(model, 8, dt, mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"], mpc["u_min"], mpc["u_max"],
+                               x_min=[-0.2, -0.05, -0.1, -0.2], x_max=[0.2, 0.05, 0.1, 0.2], optimizer_type="Adam",
+                               lr=mpc["learning_rate"], max_iterations=6)
+        out.update(ctrlb_u=np.stack([ctrl_b.compute_control(s) for s in xs]))
+        Ub = torch.zeros(8, 1)
+        st = ctrl_b.rollout_dynamics(torch.tensor(xs[1], dtype=torch.float32), Ub)
+        out.update(ctrlb_cost0=np.float32(ctrl_b.compute_cost(st, Ub).item()))
+    np.savez(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "done; H[0..2] =", out["rand_H"][:3])
+
+
+def gen_canonical():
+    torch.manual_seed(0)
+    model = pHNN_Canonical(os.path.join(CFG, "cartpole_phnn.yaml"))
+    model.eval()
+    # perturb the physical parameters so every derivative path is exercised
+    with torch.no_grad():
+        model.M_net.log_a.copy_(torch.tensor(0.25))
+        model.M_net.b.copy_(torch.tensor(0.35))
+        model.M_net.log_c.copy_(torch.tensor(-0.4))
+        model.R_diag_raw.copy_(torch.tensor([0.1, -0.3, 0.5, 1.2]))
+    cfg = yaml.safe_load(open(os.path.join(CFG, "pole_stabilization.yaml")))
+    mpc = cfg["mpc"]
+    out = sd_np(model)
+    g = torch.Generator().manual_seed(3)
+    x, u, v = cartpole_points(g, 32)
+    dx, H, gx, gu = fwd_and_vjp(model, x, u, v)
+    out.update(rand_x=x.numpy(), rand_u=u.numpy(), rand_v=v.numpy(), rand_dx=dx.numpy(), rand_H=H.numpy(),
+               rand_gx=gx.numpy(), rand_gu=gu.numpy())
+    Q = torch.diag(torch.tensor(mpc["Q_diag"]))
+    R = torch.diag(torch.tensor(mpc["R_diag"]))
+    xt = torch.tensor(mpc["x_target"])
+    dt = cfg["cartpole"]["dt"]
+    B, Hh, iters = 8, 10, 6
+    x0 = torch.tensor([0.0, 0.05, 0.0, 0.0]) + (torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])
+    U0 = (torch.rand(B, Hh, 1, generator=g) * 2 - 1) * 35.0
+    out.update(mpc_x0=x0.numpy(), mpc_U0=U0.numpy(), mpc_Q=Q.numpy(), mpc_R=R.numpy(), mpc_xt=xt.numpy(),
+               mpc_bounds=np.array([mpc["u_min"], mpc["u_max"]], np.float32), mpc_lr=np.float32(mpc["learning_rate"]),
+               mpc_dt=np.float32(dt))
+    for integ in ("euler", "rk4"):
+        res = composition_solve(model, x0, U0, dt, integ, Q, R, xt, mpc["u_min"], mpc["u_max"], mpc["learning_rate"],
+                                iters, "best")
+        for k, val in res.items():
+            out["mpc_%s_%s" % (integ, k)] = val
+    # the real canonical controller (config 3, B=1): cold start then a warm start
+    ctrl = create_mpc_controller(model, cfg)
+    xs = x0[:3].numpy().astype(np.float64)
+    us, seqs, costs = [], [], []
+    for s in xs:
+        u1, info1 = ctrl.control(s)
+        u2, info2 = ctrl.control(s + 0.01, info1["u_sequence"])
+        us.append(np.stack([u1, u2]))
+        seqs.append(np.stack([info1["u_sequence"], info2["u_sequence"]]))
+        costs.append(np.stack([np.array(info1["optimization"]["costs"], np.float32),
+                               np.array(info2["optimization"]["costs"], np.float32)]))
+    out.update(ctrl_x=xs, ctrl_u=np.stack(us), ctrl_seq=np.stack(seqs), ctrl_costs=np.stack(costs))
+    np.savez(os.path.join(HERE, "canonical.npz"), **out)
+    print("canonical done; dx[0] =", out["rand_dx"][0])
+
+
+if __name__ == "__main__":
+    gen_pendulum()
+    gen_cartpole(128, 0, "cartpole_h128")
+    gen_cartpole(256, 1234, "cartpole_h256")
+    gen_canonical()
