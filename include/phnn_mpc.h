@@ -1,0 +1,126 @@
+/*
+ * include/phnn_mpc.h -- C ABI of libphnn_mpc.so, the B200 (sm_100a) implementation of the
+ * pHNN-MPC hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * The reference (Peilun-Tommy-Li/pHNN-MPC) is pure Python and has no FFI of its own: the
+ * boundary it exposes is the Python module surface its drivers import
+ * (scripts/run_cartpole_mpc.py:21-24, scripts/run_mpc_canonical.py:18-22).  Each entry point
+ * below names the reference function whose arithmetic it replaces; the ctypes binding and the
+ * drop-in Python modules that sit on top are in phnn_mpc_b200/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 bad argument (PHNN_E_*), >0 a cudaError_t value;
+ *     phnn_last_error() returns a thread-local message for the last non-zero return.
+ *   - all data pointers are DEVICE pointers to float32, row-major, on the pack's device.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); the library keeps
+ *     no global mutable state; a pack is immutable after creation and may be shared.
+ *   - instances (rows of the leading B dimension) are independent.
+ */
+#ifndef PHNN_MPC_H
+#define PHNN_MPC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHNN_KIND_PHNN 0      /* src/pHNN.py            dx = (J - J^T - R(x)) dH + G u          */
+#define PHNN_KIND_CANONICAL 1 /* src/pHNN_canonical.py  z=[q,M(q)qd], dy = [M^-1 p, M^-1 pdot]  */
+
+#define PHNN_EULER 0 /* src/integrators.py:13-36 */
+#define PHNN_RK4 1   /* src/integrators.py:39-84 */
+
+#define PHNN_E_ARG (-1)         /* null pointer / bad size                                      */
+#define PHNN_E_UNSUPPORTED (-2) /* model shape has no kernel instantiation                      */
+#define PHNN_E_INTEGRATOR (-3)  /* unknown integrator (reference raises ValueError)             */
+#define PHNN_E_WORKSPACE (-4)   /* workspace too small                                          */
+
+/* Host-side description of one model, in the reference's state_dict layout
+ * (nn.Linear weight = [out,in] row-major).  All pointers are HOST float32.                     */
+typedef struct phnn_model_desc {
+    int kind;                                  /* PHNN_KIND_*                                   */
+    int n, m;                                  /* state_dim, input_dim (m must be 1)            */
+    int h;                                     /* hidden width: H_net [h,h]; R_net/G_net [h]     */
+    int learned_G;                             /* 1: G_net present (src/pHNN.py:34-38)           */
+    const float *W1, *b1, *W2, *b2, *W3, *b3;  /* H_net.net.{0,2,4}: [h,n] [h] [h,h] [h] [1,h] [1] */
+    const float *Wr1, *br1, *Wr2, *br2;        /* R_net.net.{0,2}:   [h,n] [h] [n*n,h] [n*n]      */
+    const float *Wg1, *bg1, *Wg2, *bg2;        /* G_net.net.{0,2}:   [h,n] [h] [n*m,h] [n*m]      */
+    const float *J;                            /* [n,n] parameter (kind 0) / buffer (kind 1)     */
+    const float *G;                            /* [n,m] G_fixed (kind 0) / G (kind 1)            */
+    float mass_a, mass_b, mass_c;              /* kind 1: exp(log_a)+1e-3, b, exp(log_c)+1e-3    */
+    const float *r_diag;                       /* kind 1: softplus(R_diag_raw)+1e-4, [n]         */
+} phnn_model_desc;
+
+/* Horizon cost of the controllers (src/mpc_controller.py:75-114,
+ * src/mpc_controller_canonical.py:91-120).  All pointers are HOST float32.                     */
+typedef struct phnn_cost_desc {
+    const float *Q;        /* [n,n]                                                             */
+    const float *R;        /* [m,m]                                                             */
+    const float *x_target; /* [n]                                                               */
+    int has_u_bounds;      /* clamp(u, u_min, u_max) inside the differentiated graph            */
+    float u_min, u_max;
+    const float *x_min;    /* optional [n] soft bounds, NULL if absent                          */
+    const float *x_max;
+    float barrier_weight;  /* 1000 in the reference                                             */
+} phnn_cost_desc;
+
+typedef struct phnn_pack phnn_pack; /* opaque: packed weights resident in HBM */
+
+const char *phnn_last_error(void);
+int phnn_version(void);
+
+/* Pack the weights of one model onto `device` (replaces nothing in the reference: it is the
+ * device-side image of pHNN.__init__/load_state_dict, src/pHNN.py:13-38).                      */
+int phnn_pack_create(const phnn_model_desc *desc, int device, phnn_pack **out);
+int phnn_pack_destroy(phnn_pack *pack);
+int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
+
+/* dx[B,n], H[B] = model(x[B,n], u[B,m])          pHNN.forward src/pHNN.py:52-100,
+ *                                                pHNN_Canonical.forward src/pHNN_canonical.py:172-273 */
+int phnn_forward(const phnn_pack *pack, const float *x, const float *u, float *dx, float *H, long B,
+                 void *stream);
+
+/* xbar[B,n], ubar[B,m] = (d dx / d(x,u))^T v     what autograd evaluates for the reference's
+ * double backward through torch.autograd.grad (src/pHNN.py:73).                                */
+int phnn_vjp(const phnn_pack *pack, const float *x, const float *u, const float *v, float *xbar,
+             float *ubar, long B, void *stream);
+
+/* traj[B,T+1,n] (and energies[B,T+1] if non-NULL) from x0[B,n], U[B,T,m].
+ * energy_mode 1: rollout_trajectory_differentiable(return_energies=True) ordering
+ *                [H(y0),H(y0),H(y1),..,H(y_{T-1})]  src/integrators.py:192-258
+ * energy_mode 2: rollout_trajectory ordering [H(y0),..,H(y_T)]  src/integrators.py:128-189     */
+int phnn_rollout(const phnn_pack *pack, const float *x0, const float *U, float *traj, float *energies,
+                 long B, int T, double dt, int integrator, int energy_mode, void *stream);
+
+/* Bytes of scratch phnn_cost_grad / phnn_mpc_solve need for (B, T).                            */
+size_t phnn_workspace_bytes(const phnn_pack *pack, long B, int T, int integrator);
+
+/* cost[B] and dJdU[B,T,m] (NULL: cost only) of the horizon cost at U[B,T,m]
+ * (MPCController.rollout_dynamics+compute_cost+backward, src/mpc_controller.py:75-141,176-194;
+ *  MPCControllerCanonical.rollout+compute_cost, src/mpc_controller_canonical.py:91-161).        */
+int phnn_cost_grad(const phnn_pack *pack, const phnn_cost_desc *cost_desc, const float *x0, const float *U,
+                   float *cost, float *dJdU, float *traj, long B, int T, double dt, int integrator,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* The whole solve: iters x { clamp, rollout, cost, adjoint, Adam step } in ONE launch.
+ * U_inout[B,T,m]: initial guess in, result out.
+ * return_mode 0: controls after the last Adam step, clamped (MPCController.compute_control,
+ *                src/mpc_controller.py:143-209)
+ * return_mode 1: clamped pre-step iterate of lowest cost (MPCControllerCanonical.optimize_control,
+ *                src/mpc_controller_canonical.py:163-228)
+ * cost_hist[iters,B] and best_cost[B] may be NULL.                                              */
+int phnn_mpc_solve(const phnn_pack *pack, const phnn_cost_desc *cost_desc, const float *x0, float *U_inout,
+                   float *cost_hist, float *best_cost, long B, int T, double dt, int integrator, double lr,
+                   double beta1, double beta2, double eps, int iters, int return_mode, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/* Measurement utility (not part of the replaced path): launches a pure FFMA kernel of `blocks`
+ * x 256 threads and returns the FLOPs it executes in *flops; bench.py times it with CUDA events
+ * to get this GPU's sustained FP32-FMA rate, the roofline denominator of the FP32 path.        */
+int phnn_ffma_probe(float *d_out, int iters, int blocks, void *stream, double *flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHNN_MPC_H */

@@ -1,0 +1,118 @@
+"""Weights of a pHNN / pHNN_Canonical module -> packed device image (phnn_pack).
+
+Accepts any module (or state_dict) with the reference's parameter names
+(src/pHNN.py:13-38: J, G_fixed | G_net.net.{0,2}.*, R_net.net.{0,2}.*, H_net.net.{0,2,4}.*;
+ src/pHNN_canonical.py:57-110: J, G, R_diag_raw, M_net.{log_a,b,log_c}, H_net.net.{0,2,4}.*),
+so reference checkpoints load unchanged.
+"""
+import ctypes
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _f32(t):
+    if isinstance(t, torch.Tensor):
+        t = t.detach().to("cpu", torch.float32).numpy()
+    return np.ascontiguousarray(np.asarray(t, dtype=np.float32))
+
+
+def infer_kind(sd):
+    return "canonical" if "R_diag_raw" in sd else "phnn"
+
+
+class PackedModel:
+    """Owns one phnn_pack handle (immutable device copy of the weights)."""
+
+    def __init__(self, state_dict, kind=None, device=None):
+        L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("phnn_mpc_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("phnn_mpc_b200 runs on CUDA devices only, got %s" % self.device)
+        sd = dict(state_dict)
+        kind = kind or infer_kind(sd)
+        keep = []
+
+        def ptr(name):
+            a = _f32(sd[name])
+            keep.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+        for i in (0, 2, 4):
+            if "H_net.net.%d.weight" % i not in sd:
+                raise RuntimeError("H_net must be Linear-Tanh-Linear-Tanh-Linear (two hidden layers, no LayerNorm/"
+                                   "Dropout); key H_net.net.%d.weight missing" % i)
+        if "H_net.net.6.weight" in sd:
+            raise RuntimeError("H_net with more than two hidden layers is not supported by the CUDA kernels")
+        W1, W2 = sd["H_net.net.0.weight"], sd["H_net.net.2.weight"]
+        d = _lib.ModelDesc()
+        d.n, d.h = int(W1.shape[1]), int(W1.shape[0])
+        if tuple(W2.shape) != (d.h, d.h):
+            raise RuntimeError("H_net hidden layers must have equal width, got %s" % (tuple(W2.shape),))
+        d.W1, d.b1 = ptr("H_net.net.0.weight"), ptr("H_net.net.0.bias")
+        d.W2, d.b2 = ptr("H_net.net.2.weight"), ptr("H_net.net.2.bias")
+        d.W3, d.b3 = ptr("H_net.net.4.weight"), ptr("H_net.net.4.bias")
+        d.J = ptr("J")
+        if kind == "phnn":
+            d.kind = _lib.PHNN_KIND_PHNN
+            if "R_net.net.4.weight" in sd or int(sd["R_net.net.0.weight"].shape[0]) != d.h:
+                raise RuntimeError("R_net must have one hidden layer of the same width as H_net (%d)" % d.h)
+            d.Wr1, d.br1 = ptr("R_net.net.0.weight"), ptr("R_net.net.0.bias")
+            d.Wr2, d.br2 = ptr("R_net.net.2.weight"), ptr("R_net.net.2.bias")
+            if "G_fixed" in sd:
+                d.learned_G = 0
+                d.m = int(sd["G_fixed"].shape[1])
+                d.G = ptr("G_fixed")
+            else:
+                d.learned_G = 1
+                if "G_net.net.4.weight" in sd or int(sd["G_net.net.0.weight"].shape[0]) != d.h:
+                    raise RuntimeError("G_net must have one hidden layer of the same width as H_net (%d)" % d.h)
+                d.m = int(sd["G_net.net.2.weight"].shape[0]) // d.n
+                d.Wg1, d.bg1 = ptr("G_net.net.0.weight"), ptr("G_net.net.0.bias")
+                d.Wg2, d.bg2 = ptr("G_net.net.2.weight"), ptr("G_net.net.2.bias")
+        elif kind == "canonical":
+            d.kind = _lib.PHNN_KIND_CANONICAL
+            d.learned_G = 0
+            d.m = int(sd["G"].shape[1])
+            d.G = ptr("G")
+            # src/mass_matrix.py:283-285 (float32 arithmetic) and src/pHNN_canonical.py:162
+            la, lc = torch.as_tensor(sd["M_net.log_a"]).float(), torch.as_tensor(sd["M_net.log_c"]).float()
+            d.mass_a = float(torch.exp(la) + 1e-3)
+            d.mass_b = float(torch.as_tensor(sd["M_net.b"]).float())
+            d.mass_c = float(torch.exp(lc) + 1e-3)
+            rd = torch.nn.functional.softplus(torch.as_tensor(sd["R_diag_raw"]).float()) + 1e-4
+            sd["__r_diag"] = rd
+            d.r_diag = ptr("__r_diag")
+        else:
+            raise ValueError("unknown model kind %r" % (kind,))
+        self.kind, self.n, self.m, self.h = kind, d.n, d.m, d.h
+        handle = ctypes.c_void_p()
+        _lib.check(L.phnn_pack_create(ctypes.byref(d), self.device.index or 0, ctypes.byref(handle)),
+                   "phnn_pack_create")
+        self.handle = handle.value
+        self._fin = weakref.finalize(self, L.phnn_pack_destroy, ctypes.c_void_p(self.handle))
+
+    def __int__(self):
+        return self.handle
+
+
+_cache = weakref.WeakKeyDictionary()
+
+
+def pack_of(module, device=None):
+    """Packed image of an nn.Module, rebuilt when any parameter/buffer changed (tracked by the
+    tensors' _version counters and data pointers)."""
+    tensors = list(module.state_dict(keep_vars=True).items())
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (str(dev),) + tuple((k, t._version, t.data_ptr()) for k, t in tensors)
+    hit = _cache.get(module)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    pk = PackedModel({k: t for k, t in tensors}, device=dev)
+    _cache[module] = (key, pk)
+    return pk

@@ -1,0 +1,206 @@
+"""GPU parity: the CUDA path (through the C ABI / torch.library ops) against
+(a) the golden vectors recorded from the reference's PyTorch-autograd implementation and
+(b) the CPU oracle on the same seeded inputs.
+
+Tolerances (FP32 path, north_star: 1e-5 per step, 1e-4 over a horizon; all relative to the
+largest entry of the compared tensor):
+  single evaluation (dx, H, VJP) ......... 1e-5
+  rollouts / cost / dJdU over a horizon .. 1e-4
+  controls after Adam .................... abs 0.02*lr + 1e-5 (early Adam steps are ~lr*sign(g))
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical"}
+STEP_TOL = 1e-5
+HORIZON_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def env():
+    from phnn_mpc_b200 import ops
+    from phnn_mpc_b200.packing import PackedModel
+    assert torch.cuda.is_available()
+    packs = {}
+
+    def get(name):
+        if name not in packs:
+            z, sd = load_golden(name)
+            packs[name] = (z, sd, PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, KINDS[name]))
+        return packs[name]
+
+    return ops, get
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def cost_args(z):
+    lo, hi = [float(v) for v in z["mpc_bounds"]]
+    return (torch.from_numpy(z["mpc_Q"]), torch.from_numpy(z["mpc_R"]), torch.from_numpy(z["mpc_xt"]), True, lo, hi,
+            None, None, 1000.0)
+
+
+@pytest.mark.parametrize("name", list(KINDS))
+def test_forward_vjp_golden(env, name):
+    ops, get = env
+    z, sd, pk = get(name)
+    dx, H = ops.forward(pk.handle, cu(z["rand_x"]), cu(z["rand_u"]))
+    assert rel_err(dx.cpu().numpy(), z["rand_dx"]) < STEP_TOL
+    assert rel_err(H.cpu().numpy(), z["rand_H"]) < STEP_TOL
+    xb, ub = ops.vjp(pk.handle, cu(z["rand_x"]), cu(z["rand_u"]), cu(z["rand_v"]))
+    assert rel_err(xb.cpu().numpy(), z["rand_gx"]) < STEP_TOL
+    assert rel_err(ub.cpu().numpy(), z["rand_gu"]) < STEP_TOL
+
+
+def test_forward_wide_states(env):
+    """states over the range of data/cartpole_training_data.pt (|x| up to ~20)"""
+    ops, get = env
+    for name in ("cartpole_h128", "cartpole_h256"):
+        z, sd, pk = get(name)
+        dx, H = ops.forward(pk.handle, cu(z["wide_x"]), cu(z["rand_u"][:16]))
+        assert rel_err(dx.cpu().numpy(), z["wide_dx"]) < STEP_TOL
+        assert rel_err(H.cpu().numpy(), z["wide_H"]) < STEP_TOL
+        xb, _ = ops.vjp(pk.handle, cu(z["wide_x"]), cu(z["rand_u"][:16]), cu(z["rand_v"][:16]))
+        assert rel_err(xb.cpu().numpy(), z["wide_gx"]) < STEP_TOL
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 100, 1000])
+def test_forward_ragged_batches_vs_oracle(env, B):
+    from oracle.phnn_oracle import OracleModel
+    ops, get = env
+    for name in KINDS:
+        z, sd, pk = get(name)
+        M = OracleModel(sd, KINDS[name])
+        rng = np.random.default_rng(B)
+        x = rng.normal(size=(B, M.n)).astype(np.float32)
+        u = rng.normal(size=(B, 1)).astype(np.float32) * 3
+        v = rng.normal(size=(B, M.n)).astype(np.float32)
+        dx, H = ops.forward(pk.handle, cu(x), cu(u))
+        dxo, Ho = M.forward(x, u)
+        assert rel_err(dx.cpu().numpy(), dxo) < STEP_TOL
+        assert rel_err(H.cpu().numpy(), Ho) < STEP_TOL
+        xb, ub = ops.vjp(pk.handle, cu(x), cu(u), cu(v))
+        xbo, ubo = M.vjp(x, u, v)
+        assert rel_err(xb.cpu().numpy(), xbo) < STEP_TOL
+        assert rel_err(ub.cpu().numpy(), ubo) < STEP_TOL
+
+
+def test_empty_batch(env):
+    ops, get = env
+    z, sd, pk = get("cartpole_h128")
+    dx, H = ops.forward(pk.handle, torch.empty(0, 4, device="cuda"), torch.empty(0, 1, device="cuda"))
+    assert dx.shape == (0, 4) and H.shape == (0,)
+
+
+def test_pendulum_anchor_rollouts(env):
+    ops, get = env
+    z, sd, pk = get("pendulum")
+    U10 = np.repeat(z["anchor_u"][:, None, :], 10, 1)
+    for integ, iid in (("rk4", 1), ("euler", 0)):
+        tr, en = ops.rollout(pk.handle, cu(z["anchor_x"]), cu(U10), 0.05, iid, 1)
+        assert rel_err(tr.cpu().numpy(), z["anchor_traj_" + integ]) < HORIZON_TOL
+        assert rel_err(en.cpu().numpy(), z["anchor_en_" + integ]) < HORIZON_TOL
+        tr2, en2 = ops.rollout(pk.handle, cu(z["anchor_x"]), cu(U10), 0.05, iid, 2)
+        assert rel_err(tr2.cpu().numpy(), z["anchor_traj2_" + integ]) < HORIZON_TOL
+        assert rel_err(en2.cpu().numpy(), z["anchor_en2_" + integ]) < HORIZON_TOL
+    tr, _ = ops.rollout(pk.handle, cu(z["anchor_x"]), cu(U10), 0.05, 1, 0)
+    np.testing.assert_allclose(tr[:, -1].cpu().numpy(), [[0.300435662, -2.837836504], [-0.848876774, 4.260723591]],
+                               rtol=2e-5)
+
+
+@pytest.mark.parametrize("integ", ["rk4", "euler"])
+def test_pendulum_cfg2_rollout(env, integ):
+    """BASELINE config 2 inputs (first 64 instances) against the reference's own rollout."""
+    ops, get = env
+    z, sd, pk = get("pendulum")
+    tr, en = ops.rollout(pk.handle, cu(z["cfg2_x0"]), cu(z["cfg2_U"]), 0.05, {"euler": 0, "rk4": 1}[integ], 1)
+    assert rel_err(tr.cpu().numpy(), z["cfg2_traj_" + integ]) < HORIZON_TOL
+    assert rel_err(en.cpu().numpy(), z["cfg2_en_" + integ]) < HORIZON_TOL
+
+
+@pytest.mark.parametrize("name", list(KINDS))
+@pytest.mark.parametrize("integ", ["euler", "rk4"])
+def test_cost_grad_and_solve_golden(env, name, integ):
+    ops, get = env
+    z, sd, pk = get(name)
+    iid = {"euler": 0, "rk4": 1}[integ]
+    dt, lr = float(z["mpc_dt"]), float(z["mpc_lr"])
+    ca = cost_args(z)
+    p = "mpc_%s_" % integ
+    cost, g, tr = ops.cost_grad(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, True, True)
+    assert rel_err(cost.cpu().numpy(), z[p + "hist"][0]) < HORIZON_TOL
+    assert rel_err(g.cpu().numpy(), z[p + "grad0"]) < HORIZON_TOL
+    if p + "traj0" in z.files:
+        assert rel_err(tr.cpu().numpy(), z[p + "traj0"]) < HORIZON_TOL
+    lo, hi = [float(v) for v in z["mpc_bounds"]]
+    out = (z["mpc_U0"] < lo) | (z["mpc_U0"] > hi)
+    assert out.any() and np.all(g.cpu().numpy()[out] == 0)
+    iters = z[p + "hist"].shape[0]
+    for mode, key in ((0, "U_last"), (1, "U_best")):
+        U, hist, best = ops.mpc_solve(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, lr, 0.9, 0.999, 1e-8,
+                                      iters, mode, True)
+        assert rel_err(hist.cpu().numpy(), z[p + "hist"]) < HORIZON_TOL
+        assert np.abs(U.cpu().numpy() - z[p + key]).max() < 0.02 * lr + 1e-5
+        assert rel_err(best.cpu().numpy(), z[p + "best"]) < HORIZON_TOL
+
+
+@pytest.mark.parametrize("name,H,integ", [("cartpole_h256", 50, "rk4"), ("cartpole_h256", 50, "euler"),
+                                          ("cartpole_h128", 20, "euler"), ("canonical", 10, "euler"),
+                                          ("pendulum", 30, "rk4")])
+def test_solve_vs_oracle_batched(env, name, H, integ):
+    """BASELINE config 3/4-shaped work on a 96-instance sub-sample against the CPU oracle."""
+    from oracle.phnn_oracle import OracleModel
+    ops, get = env
+    z, sd, pk = get(name)
+    M = OracleModel(sd, KINDS[name])
+    B, iters = 96, 4
+    g = torch.Generator().manual_seed(7)
+    n = M.n
+    scale = torch.tensor([1.0, 0.3, 0.5, 0.5][:n])
+    x0 = ((torch.rand(B, n, generator=g) * 2 - 1) * scale).numpy()
+    U0 = ((torch.rand(B, H, 1, generator=g) * 2 - 1) * 3).numpy()
+    Q = np.diag([10.0, 200.0, 1.0, 10.0][:n]).astype(np.float32)
+    R = np.array([[0.01]], np.float32)
+    xt = np.zeros(n, np.float32)
+    C = M.cost_struct(Q, R, xt, -15.0, 15.0)
+    Jo, go = M.cost_grad(C, x0, U0, 0.02, integ)
+    iid = {"euler": 0, "rk4": 1}[integ]
+    ca = (torch.from_numpy(Q), torch.from_numpy(R), torch.from_numpy(xt), True, -15.0, 15.0, None, None, 1000.0)
+    cost, gg, _ = ops.cost_grad(pk.handle, cu(x0), cu(U0), 0.02, iid, *ca, True, False)
+    assert rel_err(cost.cpu().numpy(), Jo) < HORIZON_TOL
+    assert rel_err(gg.cpu().numpy(), go) < HORIZON_TOL
+    Uo, histo, besto = M.mpc_solve(C, x0, U0, 0.02, integ, lr=0.015, iters=iters, return_mode="last")
+    U, hist, best = ops.mpc_solve(pk.handle, cu(x0), cu(U0), 0.02, iid, *ca, 0.015, 0.9, 0.999, 1e-8, iters, 0, True)
+    assert rel_err(hist.cpu().numpy(), histo) < HORIZON_TOL
+    assert np.abs(U.cpu().numpy() - Uo).max() < 0.02 * 0.015 + 1e-5
+
+
+def test_state_barrier_cost(env):
+    """optional soft state bounds of MPCController (src/mpc_controller.py:96-107)"""
+    ops, get = env
+    z, sd, pk = get("cartpole_h128")
+    x = cu(z["ctrl_x"][1:2])
+    Q = torch.diag(torch.tensor([10.0, 200.0, 1.0, 10.0]))
+    R = torch.tensor([[0.01]])
+    xmin = torch.tensor([-0.2, -0.05, -0.1, -0.2])
+    xmax = torch.tensor([0.2, 0.05, 0.1, 0.2])
+    cost, _, _ = ops.cost_grad(pk.handle, x, torch.zeros(1, 8, 1, device="cuda"), 0.02, 0, Q, R, torch.zeros(4), True,
+                               -15.0, 15.0, xmin, xmax, 1000.0, False, False)
+    assert abs(cost.item() - float(z["ctrlb_cost0"])) / float(z["ctrlb_cost0"]) < HORIZON_TOL
+    U, _, _ = ops.mpc_solve(pk.handle, cu(z["ctrl_x"]), torch.zeros(3, 8, 1, device="cuda"), 0.02, 0, Q, R,
+                            torch.zeros(4), True, -15.0, 15.0, xmin, xmax, 1000.0, 0.015, 0.9, 0.999, 1e-8, 6, 0, False)
+    assert np.abs(U[:, 0].cpu().numpy() - z["ctrlb_u"]).max() < 0.02 * 0.015
+
+
+def test_unknown_integrator_raises(env):
+    ops, get = env
+    z, sd, pk = get("cartpole_h128")
+    with pytest.raises(ValueError):
+        ops.rollout(pk.handle, cu(z["rand_x"]), torch.zeros(32, 3, 1, device="cuda"), 0.02, 7, 0)
