@@ -36,8 +36,9 @@ WORKLOADS = {
              "BASELINE cfg3: canonical pHNN pole-stabilisation MPC, 1024 instances x H=10 x 50 iters, Euler"),
     "cfg5_h100": ("cartpole_h256", "phnn", 131072, 100, 20, "rk4", 0.015,
                   "BASELINE cfg5 shard: 1M/8 instances x H=100 x 20 iters, RK4, hidden 256"),
-    "small": ("cartpole_h256", "phnn", 4736, 50, 4, "rk4", 0.015,
-              "profiling-sized cfg4 slice: 4736 instances x H=50 x 4 iters, RK4, hidden 256"),
+    "small": ("cartpole_h256", "phnn", 9472, 50, 2, "rk4", 0.015,
+              "profiling-sized cfg4 slice (one full wave, 64 instances per SM): 9472 instances x H=50 x 2 iters, "
+              "RK4, hidden 256"),
 }
 
 

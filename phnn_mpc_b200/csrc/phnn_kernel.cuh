@@ -141,6 +141,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -161,15 +172,18 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// tanh to ~2e-7 absolute: 1 - 2/(exp(2x)+1) with MUFU.EX2 + MUFU.RCP.  tanh.approx (2^-11) would
-// break the 1e-5 per-step tolerance ("Accurate tanh").
+// tanh: the accurate libdevice tanhf (branch-free on sm_100a: a degree-7 odd polynomial below
+// |x| = 0.6, 1 - 2/(exp(2x)+1) with MUFU.EX2/MUFU.RCP above; ~14 instructions, ~1 ulp).
+// tanh.approx.f32 (2^-11) would break the 1e-5 per-step tolerance, and the
+// 5-instruction 1 - 2/(exp(2x)+1) form alone (PHNN_TANH_FAST, ~2e-7 absolute) measured 2x the
+// horizon error of tanhf on the 100-step pendulum rollout for ~4% less time, so it is opt-in.
 __device__ __forceinline__ float tanh_acc(float x) {
-#ifdef PHNN_TANH_LIBM
-    return tanhf(x);
-#else
+#ifdef PHNN_TANH_FAST
     const float e = ex2_approx(x * 2.8853900817779268f);
     const float r = rcp_approx(e + 1.0f);
     return fmaf(-2.0f, r, 1.0f);
+#else
+    return tanhf(x);
 #endif
 }
 
@@ -196,19 +210,28 @@ __device__ __forceinline__ void lane8_reduce(float* v, int lo) {
 // ---------------------------------------------------------------------------------------
 // per-thread context
 // ---------------------------------------------------------------------------------------
+// Dynamic shared memory of the CTA.  Everything is addressed as (this symbol + offset) so the
+// compiler emits shared-space LDS/STS with 32-bit addresses instead of generic LD/ST (the first
+// ncu capture showed LD.E.128 in the product loop and ~20% long-scoreboard stalls on them).
+extern __shared__ __align__(128) unsigned char phnn_smem[];
+
 template <class SH>
 struct Ctx {
-    const float* wsm;  // small weights in smem
-    const float* ring;
-    float* bufA;
-    float* bufB;
-    float* part;
-    float* rbar;
-    uint64_t* full;
-    uint64_t* empty;
+    uint32_t goff;  // float offset of this group's region
     int lane, li, lo, wg, barid, wcol, chunk;
     uint32_t tile;  // ring tiles consumed so far
+    bool ready;     // the next ring stage was already seen full by an early poll
     bool store;     // this warp performs the group's global stores
+
+    __device__ __forceinline__ float* smf() const { return reinterpret_cast<float*>(phnn_smem + 128); }
+    __device__ __forceinline__ const float* wsm() const { return smf(); }
+    __device__ __forceinline__ const float* ring() const { return smf() + SH::SMALL; }
+    __device__ __forceinline__ float* bufA() const { return smf() + goff + SH::G_BUFA; }
+    __device__ __forceinline__ float* bufB() const { return smf() + goff + SH::G_BUFB; }
+    __device__ __forceinline__ float* part() const { return smf() + goff + SH::G_PART; }
+    __device__ __forceinline__ float* rbar() const { return smf() + goff + SH::G_RBAR; }
+    __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(phnn_smem); }
+    __device__ __forceinline__ uint64_t* empty() const { return full() + NST; }
 
     __device__ __forceinline__ void gbar() const {
         if (SH::NWG == 1) __syncwarp();
@@ -232,8 +255,14 @@ __device__ __forceinline__ void product(Ctx<SH>& c, const float* __restrict__ lh
     for (int t = 0; t < HID / KT; ++t) {
         const uint32_t s = c.tile % NST;
         const uint32_t ph = (c.tile / NST) & 1u;
-        mbar_wait(&c.full[s], ph);
-        const float* __restrict__ wst = c.ring + s * (KT * HID) + c.wcol;
+        if (!c.ready) mbar_wait(&c.full()[s], ph);
+        // poll the next stage now; the answer is consumed after this stage's FFMAs, which hides
+        // the ~90-cycle try_wait latency the first capture showed at the top of every stage
+        {
+            const uint32_t s2 = (c.tile + 1) % NST, ph2 = ((c.tile + 1) / NST) & 1u;
+            c.ready = mbar_try(&c.full()[s2], ph2);
+        }
+        const float* __restrict__ wst = c.ring() + s * (KT * HID) + c.wcol;
         const int k0 = t * KT;
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
@@ -250,7 +279,7 @@ __device__ __forceinline__ void product(Ctx<SH>& c, const float* __restrict__ lh
                 for (int o = 0; o < 8; ++o) acc[r][o] = fmaf(a[r], w[o], acc[r][o]);
         }
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.empty[s]);
+        if (c.lane == 0) mbar_arrive(&c.empty()[s]);
         ++c.tile;
     }
 }
@@ -313,7 +342,7 @@ __device__ __forceinline__ void load_S(const Ctx<SH>& c, const KParams& p, float
     for (int e = 0; e < NN; ++e) {
         float s = p.br2[e];
 #pragma unroll
-        for (int w = 0; w < SH::NWG; ++w) s += c.part[(w * 32 + c.lane) * SH::PW + SH::SL_R + e];
+        for (int w = 0; w < SH::NWG; ++w) s += c.part()[(w * 32 + c.lane) * SH::PW + SH::SL_R + e];
         Rraw[e] = s;
     }
 #pragma unroll
@@ -328,7 +357,7 @@ __device__ __forceinline__ void load_part(const Ctx<SH>& c, float (&out)[N]) {
     for (int e = 0; e < N; ++e) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < SH::NWG; ++w) s += c.part[(w * 32 + c.lane) * SH::PW + SLOT + e];
+        for (int w = 0; w < SH::NWG; ++w) s += c.part()[(w * 32 + c.lane) * SH::PW + SLOT + e];
         out[e] = s;
     }
 }
@@ -345,25 +374,25 @@ __device__ __forceinline__ void layer1_and_aux(Ctx<SH>& c, const float (&zi)[8][
         const int k = c.kown(o);
         float w1[NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) w1[i] = c.wsm[SH::O_W1 + k * NS + i];
-        const float b1 = c.wsm[SH::O_B1 + k];
+        for (int i = 0; i < NS; ++i) w1[i] = c.wsm()[SH::O_W1 + k * NS + i];
+        const float b1 = c.wsm()[SH::O_B1 + k];
         float av[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) av[r] = tanh_acc(dotn<NS>(w1, zi[r], b1));
-        st8(c.row_own(c.bufA, k), av);
+        st8(c.row_own(c.bufA(), k), av);
         if constexpr (SH::HAS_R) {
             float wr[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) wr[i] = c.wsm[SH::O_WR1 + k * NS + i];
-            const float br = c.wsm[SH::O_BR1 + k];
+            for (int i = 0; i < NS; ++i) wr[i] = c.wsm()[SH::O_WR1 + k * NS + i];
+            const float br = c.wsm()[SH::O_BR1 + k];
 #pragma unroll
             for (int r = 0; r < 8; ++r) r1[r][o] = tanh_acc(dotn<NS>(wr, yi[r], br));
         }
         if constexpr (SH::HAS_GNET) {
             float wg_[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) wg_[i] = c.wsm[SH::O_WG1 + k * NS + i];
-            const float bg = c.wsm[SH::O_BG1 + k];
+            for (int i = 0; i < NS; ++i) wg_[i] = c.wsm()[SH::O_WG1 + k * NS + i];
+            const float bg = c.wsm()[SH::O_BG1 + k];
 #pragma unroll
             for (int r = 0; r < 8; ++r) ag[r][o] = tanh_acc(dotn<NS>(wg_, yi[r], bg));
         }
@@ -376,7 +405,7 @@ __device__ __forceinline__ void layer1_and_aux(Ctx<SH>& c, const float (&zi)[8][
 #pragma unroll
             for (int cc = 0; cc < CH; ++cc) {
                 float w[8];
-                ldw8(c, c.wsm + SH::O_WR2 + (pass * CH + cc) * HID, w);
+                ldw8(c, c.wsm() + SH::O_WR2 + (pass * CH + cc) * HID, w);
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     float s = 0.f;
@@ -387,7 +416,7 @@ __device__ __forceinline__ void layer1_and_aux(Ctx<SH>& c, const float (&zi)[8][
             }
             lane8_reduce<8 * CH>(P, c.lo);
 #pragma unroll
-            for (int cc = 0; cc < CH; ++cc) c.part[(c.wg * 32 + c.lane) * SH::PW + SH::SL_R + pass * CH + cc] = P[cc];
+            for (int cc = 0; cc < CH; ++cc) c.part()[(c.wg * 32 + c.lane) * SH::PW + SH::SL_R + pass * CH + cc] = P[cc];
         }
     }
     if constexpr (SH::HAS_GNET) {
@@ -395,7 +424,7 @@ __device__ __forceinline__ void layer1_and_aux(Ctx<SH>& c, const float (&zi)[8][
 #pragma unroll
         for (int a = 0; a < NS; ++a) {
             float w[8];
-            ldw8(c, c.wsm + SH::O_WG2 + a * HID, w);
+            ldw8(c, c.wsm() + SH::O_WG2 + a * HID, w);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 float s = 0.f;
@@ -406,7 +435,7 @@ __device__ __forceinline__ void layer1_and_aux(Ctx<SH>& c, const float (&zi)[8][
         }
         lane8_reduce<8 * NS>(P, c.lo);
 #pragma unroll
-        for (int a = 0; a < NS; ++a) c.part[(c.wg * 32 + c.lane) * SH::PW + SH::SL_G + a] = P[a];
+        for (int a = 0; a < NS; ++a) c.part()[(c.wg * 32 + c.lane) * SH::PW + SH::SL_G + a] = P[a];
     }
 }
 
@@ -438,7 +467,7 @@ __device__ __noinline__ void eval_fwd(Ctx<SH>& c, const KParams& p, const float 
     }
     c.gbar();  // F1: bufA, aux partials visible
     float acc[8][8];
-    product(c, c.bufA, acc);  // z2 = W2 a1
+    product(c, c.bufA(), acc);  // z2 = W2 a1
     {
         float hp[8];
 #pragma unroll
@@ -446,7 +475,7 @@ __device__ __noinline__ void eval_fwd(Ctx<SH>& c, const KParams& p, const float 
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
             const int j = c.kown(o);
-            const float b2 = c.wsm[SH::O_B2 + j], w3 = c.wsm[SH::O_W3 + j];
+            const float b2 = c.wsm()[SH::O_B2 + j], w3 = c.wsm()[SH::O_W3 + j];
             float d2[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -454,13 +483,13 @@ __device__ __noinline__ void eval_fwd(Ctx<SH>& c, const KParams& p, const float 
                 hp[r] = fmaf(w3, a2, hp[r]);
                 d2[r] = fmaf(-a2, a2, 1.f) * w3;
             }
-            st8(c.row_own(c.bufB, j), d2);
+            st8(c.row_own(c.bufB(), j), d2);
         }
         lane8_reduce<8>(hp, c.lo);
-        c.part[(c.wg * 32 + c.lane) * SH::PW + SH::SL_H] = hp[0];
+        c.part()[(c.wg * 32 + c.lane) * SH::PW + SH::SL_H] = hp[0];
     }
     c.gbar();             // F2: bufB visible
-    product(c, c.bufB, acc);  // g1 = W2^T delta2
+    product(c, c.bufB(), acc);  // g1 = W2^T delta2
     {
         float gp[8 * NS];
 #pragma unroll
@@ -469,10 +498,10 @@ __device__ __noinline__ void eval_fwd(Ctx<SH>& c, const KParams& p, const float 
         for (int o = 0; o < 8; ++o) {
             const int k = c.kown(o);
             float a1[8];
-            ld8(c.row_own(c.bufA, k), a1);
+            ld8(c.row_own(c.bufA(), k), a1);
             float w1[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) w1[i] = c.wsm[SH::O_W1 + k * NS + i];
+            for (int i = 0; i < NS; ++i) w1[i] = c.wsm()[SH::O_W1 + k * NS + i];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const float d1 = fmaf(-a1[r], a1[r], 1.f) * acc[r][o];
@@ -482,7 +511,7 @@ __device__ __noinline__ void eval_fwd(Ctx<SH>& c, const KParams& p, const float 
         }
         lane8_reduce<8 * NS>(gp, c.lo);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) c.part[(c.wg * 32 + c.lane) * SH::PW + SH::SL_DH + i] = gp[i];
+        for (int i = 0; i < NS; ++i) c.part()[(c.wg * 32 + c.lane) * SH::PW + SH::SL_DH + i] = gp[i];
     }
     c.gbar();  // F3: all partials visible
     float g[NS], hs[1];
@@ -592,11 +621,11 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
         }
     }
     float acc[8][8], keep[8][8];
-    product(c, c.bufA, acc);  // z2 = W2 a1
+    product(c, c.bufA(), acc);  // z2 = W2 a1
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
         const int j = c.kown(o);
-        const float b2 = c.wsm[SH::O_B2 + j], w3 = c.wsm[SH::O_W3 + j];
+        const float b2 = c.wsm()[SH::O_B2 + j], w3 = c.wsm()[SH::O_W3 + j];
         float d2[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -604,7 +633,7 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
             keep[r][o] = a2;
             d2[r] = fmaf(-a2, a2, 1.f) * w3;
         }
-        st8(c.row_own(c.bufB, j), d2);
+        st8(c.row_own(c.bufB(), j), d2);
     }
     c.gbar();  // A2: every warp is done reading a1 from bufA
     float wi[8][NS];
@@ -613,19 +642,19 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
     for (int o = 0; o < 8; ++o) {  // da1 = (1 - a1^2) * (W1 w) -> bufA (own elements)
         const int k = c.kown(o);
         float a1[8];
-        ld8(c.row_own(c.bufA, k), a1);
+        ld8(c.row_own(c.bufA(), k), a1);
         float w1[NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) w1[i] = c.wsm[SH::O_W1 + k * NS + i];
+        for (int i = 0; i < NS; ++i) w1[i] = c.wsm()[SH::O_W1 + k * NS + i];
 #pragma unroll
         for (int r = 0; r < 8; ++r) a1[r] = fmaf(-a1[r], a1[r], 1.f) * dotn<NS>(w1, wi[r], 0.f);
-        st8(c.row_own(c.bufA, k), a1);
+        st8(c.row_own(c.bufA(), k), a1);
     }
     c.gbar();  // A3
-    product(c, c.bufA, acc);  // dz2 = W2 da1
+    product(c, c.bufA(), acc);  // dz2 = W2 da1
 #pragma unroll
     for (int o = 0; o < 8; ++o) {  // e2 = d(s2)/dt * w3 = -2 a2 da2 w3
-        const float w3 = c.wsm[SH::O_W3 + c.kown(o)];
+        const float w3 = c.wsm()[SH::O_W3 + c.kown(o)];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const float a2 = keep[r][o];
@@ -633,17 +662,17 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
             keep[r][o] = -2.f * a2 * da2 * w3;
         }
     }
-    product(c, c.bufB, acc);  // g1 = W2^T delta2
+    product(c, c.bufB(), acc);  // g1 = W2^T delta2
     c.gbar();                 // A4: every warp is done reading delta2 from bufB
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
         float e2[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) { e2[r] = keep[r][o]; keep[r][o] = acc[r][o]; }
-        st8(c.row_own(c.bufB, c.kown(o)), e2);
+        st8(c.row_own(c.bufB(), c.kown(o)), e2);
     }
     c.gbar();  // A5
-    product(c, c.bufB, acc);  // dg1 = W2^T e2
+    product(c, c.bufB(), acc);  // dg1 = W2^T e2
     // final elementwise stage: xbar_H partials and dH partials
     float xp[8 * NS];
     float zi[8][NS];
@@ -657,10 +686,10 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
             const int k = c.kown(o);
             float w1[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) w1[i] = c.wsm[SH::O_W1 + k * NS + i];
-            const float b1 = c.wsm[SH::O_B1 + k];
+            for (int i = 0; i < NS; ++i) w1[i] = c.wsm()[SH::O_W1 + k * NS + i];
+            const float b1 = c.wsm()[SH::O_B1 + k];
             float da1[8];
-            ld8(c.row_own(c.bufA, k), da1);
+            ld8(c.row_own(c.bufA(), k), da1);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const float a1 = tanh_acc(dotn<NS>(w1, zi[r], b1));
@@ -678,7 +707,7 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
         }
         lane8_reduce<8 * NS>(gp, c.lo);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) c.part[(c.wg * 32 + c.lane) * SH::PW + SH::SL_DH + i] = gp[i];
+        for (int i = 0; i < NS; ++i) c.part()[(c.wg * 32 + c.lane) * SH::PW + SH::SL_DH + i] = gp[i];
     }
     float G[NS];
     if constexpr (SH::MK != MK_CANON) {
@@ -709,11 +738,11 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
             for (int a = 0; a < NS; ++a)
 #pragma unroll
                 for (int b = 0; b < NS; ++b)
-                    c.rbar[(a * NS + b) * GI + c.lane] =
+                    c.rbar()[(a * NS + b) * GI + c.lane] =
                         -0.5f * (v[a] * tg[b] + g[a] * sv[b] + v[b] * tg[a] + g[b] * sv[a]);
             if constexpr (SH::HAS_GNET) {
 #pragma unroll
-                for (int a = 0; a < NS; ++a) c.rbar[(NN + a) * GI + c.lane] = v[a] * u;
+                for (int a = 0; a < NS; ++a) c.rbar()[(NN + a) * GI + c.lane] = v[a] * u;
             }
         }
         c.gbar();  // A7: rbar visible
@@ -726,8 +755,8 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
 #pragma unroll
         for (int e = 0; e < NN; ++e) {
             float a[8], wv[8];
-            ld8(c.rbar + e * GI + (c.li << 3), a);
-            ldw8(c, c.wsm + SH::O_WR2 + e * HID, wv);
+            ld8(c.rbar() + e * GI + (c.li << 3), a);
+            ldw8(c, c.wsm() + SH::O_WR2 + e * HID, wv);
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -738,8 +767,8 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
             const int k = c.kown(o);
             float wr[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) wr[i] = c.wsm[SH::O_WR1 + k * NS + i];
-            const float br = c.wsm[SH::O_BR1 + k];
+            for (int i = 0; i < NS; ++i) wr[i] = c.wsm()[SH::O_WR1 + k * NS + i];
+            const float br = c.wsm()[SH::O_BR1 + k];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const float r1 = tanh_acc(dotn<NS>(wr, zi[r], br));
@@ -756,8 +785,8 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
 #pragma unroll
             for (int e = 0; e < NS; ++e) {
                 float a[8], wv[8];
-                ld8(c.rbar + (NN + e) * GI + (c.li << 3), a);
-                ldw8(c, c.wsm + SH::O_WG2 + e * HID, wv);
+                ld8(c.rbar() + (NN + e) * GI + (c.li << 3), a);
+                ldw8(c, c.wsm() + SH::O_WG2 + e * HID, wv);
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -768,8 +797,8 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
                 const int k = c.kown(o);
                 float wr[NS];
 #pragma unroll
-                for (int i = 0; i < NS; ++i) wr[i] = c.wsm[SH::O_WG1 + k * NS + i];
-                const float br = c.wsm[SH::O_BG1 + k];
+                for (int i = 0; i < NS; ++i) wr[i] = c.wsm()[SH::O_WG1 + k * NS + i];
+                const float br = c.wsm()[SH::O_BG1 + k];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const float a = tanh_acc(dotn<NS>(wr, zi[r], br));
@@ -782,7 +811,7 @@ __device__ __noinline__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float 
     }
     lane8_reduce<8 * NS>(xp, c.lo);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) c.part[(c.wg * 32 + c.lane) * SH::PW + SH::SL_X + i] = xp[i];
+    for (int i = 0; i < NS; ++i) c.part()[(c.wg * 32 + c.lane) * SH::PW + SH::SL_X + i] = xp[i];
     c.gbar();  // A8: xbar (and, canonical, dH) partials visible
     float zb[NS];
     load_part<SH, SH::SL_X, NS>(c, zb);
@@ -876,12 +905,10 @@ __device__ __forceinline__ float clampu(const KParams& p, float u) {
 template <int MK, int NS, int HID>
 __global__ void __launch_bounds__(MAX_THREADS, 1) phnn_kernel(const __grid_constant__ KParams p) {
     using SH = Shape<MK, NS, HID>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [0,NST) full, [NST,2NST) empty, [2NST] small
-    float* sm = reinterpret_cast<float*>(smem_raw + 128);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);  // [0,NST) full, [NST,2NST) empty, [2NST] small
+    float* sm = reinterpret_cast<float*>(phnn_smem + 128);
     float* wsm = sm;
     float* ring = sm + SH::SMALL;
-    float* gsm = ring + SH::RING;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = p.ng * SH::NWG;  // consumer warps
@@ -947,16 +974,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) phnn_kernel(const __grid_const
     c.wcol = 64 * c.wg + 4 * c.lo;
     c.chunk = c.li ^ (c.lo & 3);
     c.tile = 0;
+    c.ready = false;
     c.store = (c.wg == 0);
-    c.wsm = wsm;
-    c.ring = ring;
-    float* gs = gsm + grp * SH::G_FLOATS;
-    c.bufA = gs + SH::G_BUFA;
-    c.bufB = gs + SH::G_BUFB;
-    c.part = gs + SH::G_PART;
-    c.rbar = gs + SH::G_RBAR;
-    c.full = bars;
-    c.empty = bars + NST;
+    c.goff = SH::SMALL + SH::RING + grp * SH::G_FLOATS;
     mbar_wait(&bars[2 * NST], 0);  // small weights landed
 
     const long long gg = (long long)blockIdx.x * p.ng + grp;  // global group index

@@ -1,0 +1,161 @@
+"""GPU: the drop-in modules (reference names/signatures) against the golden outputs of the
+reference's own controllers and integrators."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from conftest import CONFIGS, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(kind, name, cfg="cartpole_phnn.yaml"):
+    from phnn_mpc_b200.dropin.pHNN import pHNN
+    from phnn_mpc_b200.dropin.pHNN_canonical import pHNN_Canonical
+    z, sd = load_golden(name)
+    m = (pHNN if kind == "phnn" else pHNN_Canonical)(os.path.join(CONFIGS, cfg))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return z, m
+
+
+def test_phnn_forward_module_cpu_tensors_in_out():
+    z, m = _model("phnn", "cartpole_h128")
+    dx, H = m(torch.from_numpy(z["rand_x"]), torch.from_numpy(z["rand_u"]))
+    assert dx.device.type == "cpu" and dx.shape == (32, 4) and H.shape == (32,)
+    assert rel_err(dx.numpy(), z["rand_dx"]) < 1e-5 and rel_err(H.numpy(), z["rand_H"]) < 1e-5
+    # 1-D input and the driver's logging call shape (scripts/run_cartpole_mpc.py:133-136)
+    dx1, H1 = m(torch.from_numpy(z["rand_x"][0]), torch.from_numpy(z["rand_u"][0]))
+    assert dx1.shape == (1, 4) and H1.shape == (1,)
+    s = torch.tensor(z["rand_x"][:1], requires_grad=True)
+    _, Hs = m(s, torch.tensor(z["rand_u"][:1]))
+    assert abs(Hs.item() - z["rand_H"][0]) < 1e-5 * max(1, abs(z["rand_H"][0]))
+    # [1,1,1]-shaped control as the canonical controller passes it (Appendix B.3)
+    dx3, _ = m(torch.from_numpy(z["rand_x"][:1]), torch.from_numpy(z["rand_u"][:1]).reshape(1, 1, 1))
+    assert rel_err(dx3.numpy(), z["rand_dx"][:1]) < 1e-5
+
+
+def test_forward_autograd_first_order():
+    z, m = _model("phnn", "cartpole_h128")
+    x = torch.tensor(z["rand_x"], device="cuda", requires_grad=True)
+    u = torch.tensor(z["rand_u"], device="cuda", requires_grad=True)
+    dx, _ = m(x, u)
+    (dx * torch.tensor(z["rand_v"], device="cuda")).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), z["rand_gx"]) < 1e-5
+    assert rel_err(u.grad.cpu().numpy(), z["rand_gu"]) < 1e-5
+
+
+def test_weights_repacked_after_update():
+    z, m = _model("phnn", "cartpole_h128")
+    x, u = torch.from_numpy(z["rand_x"]), torch.from_numpy(z["rand_u"])
+    dx0, _ = m(x, u)
+    with torch.no_grad():
+        m.J.mul_(2.0)
+    dx1, _ = m(x, u)
+    assert not torch.allclose(dx0, dx1)
+    with torch.no_grad():
+        m.J.mul_(0.5)
+    dx2, _ = m(x, u)
+    assert torch.equal(dx0, dx2)
+
+
+def test_canonical_forward_module():
+    z, m = _model("canonical", "canonical")
+    dy, H, aux = m(torch.from_numpy(z["rand_x"]), torch.from_numpy(z["rand_u"]))
+    assert aux is None and rel_err(dy.numpy(), z["rand_dx"]) < 1e-5 and rel_err(H.numpy(), z["rand_H"]) < 1e-5
+    dy2, _, aux2 = m(torch.from_numpy(z["rand_x"]), torch.from_numpy(z["rand_u"]), return_intermediate=True)
+    assert set(("z", "q", "p", "q_dot_reconstructed", "R")) <= set(aux2)
+    assert torch.allclose(aux2["q_dot_reconstructed"], dy2[:, :2])
+
+
+def test_integrators_dropin_pendulum():
+    from phnn_mpc_b200.dropin import integrators as I
+    z, m = _model("phnn", "pendulum", "pendulum_phnn.yaml")
+    x, u = torch.from_numpy(z["anchor_x"]), torch.from_numpy(z["anchor_u"])
+    U10 = u[:, None, :].repeat(1, 10, 1)
+    tr, en = I.rollout_trajectory_differentiable(m, x, U10, 0.05, "rk4", return_energies=True)
+    assert rel_err(tr.numpy(), z["anchor_traj_rk4"]) < 1e-4 and rel_err(en.numpy(), z["anchor_en_rk4"]) < 1e-4
+    tr2, en2 = I.rollout_trajectory(m, x, U10, 0.05, "euler")
+    assert rel_err(tr2.numpy(), z["anchor_traj2_euler"]) < 1e-4 and rel_err(en2.numpy(), z["anchor_en2_euler"]) < 1e-4
+    y1 = I.rk4_step(m, x, u, 0.05)
+    assert rel_err(y1.numpy(), z["anchor_traj_rk4"][:, 1]) < 1e-5
+    y1e = I.euler_step(m, x, u, 0.05)
+    assert rel_err(y1e.numpy(), z["anchor_traj_euler"][:, 1]) < 1e-5
+    y1b, H0 = I.rk4_step_with_energy(m, x, u, 0.05)
+    assert torch.equal(y1b, y1) and rel_err(H0.numpy(), z["anchor_H"]) < 1e-5
+    with pytest.raises(ValueError):
+        I.rollout_trajectory(m, x, U10, 0.05, "midpoint")
+
+
+def test_mpc_controller_compute_control_cfg1():
+    """BASELINE config 1: MPCController.compute_control, B=1, YAML parameters."""
+    from phnn_mpc_b200.dropin.mpc_controller import MPCController
+    z, m = _model("phnn", "cartpole_h128")
+    mpc = yaml.safe_load(open(os.path.join(CONFIGS, "cartpole_phnn.yaml")))["mpc"]
+    c = MPCController(m, mpc["horizon"], 0.02, mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"], mpc["u_min"],
+                      mpc["u_max"], optimizer_type="Adam", lr=mpc["learning_rate"], max_iterations=mpc["optimizer_steps"])
+    for s, uref in zip(z["ctrl_x"], z["ctrl_u"]):
+        u = c.compute_control(s)
+        assert isinstance(u, np.ndarray) and u.dtype == np.float32 and u.shape == (1,)
+        assert abs(u[0] - uref[0]) < 0.02 * mpc["learning_rate"]
+    out = c.solve_batch(z["ctrl_x"])                       # the same three solves as one launch
+    assert np.abs(out["u0"].cpu().numpy() - z["ctrl_u"]).max() < 0.02 * mpc["learning_rate"]
+    # helper methods of the reference's public surface
+    x0 = torch.tensor(z["ctrl_x"][1], dtype=torch.float32)
+    st = c.rollout_dynamics(x0, torch.zeros(20, 1))
+    assert st.shape == (21, 4) and torch.allclose(st[0], x0)
+    cb = MPCController(m, 8, 0.02, mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"], mpc["u_min"], mpc["u_max"],
+                       x_min=[-0.2, -0.05, -0.1, -0.2], x_max=[0.2, 0.05, 0.1, 0.2], lr=mpc["learning_rate"],
+                       max_iterations=6)
+    ub = np.stack([cb.compute_control(s) for s in z["ctrl_x"]])
+    assert np.abs(ub - z["ctrlb_u"]).max() < 0.02 * mpc["learning_rate"]
+    cost0 = cb.compute_cost(cb.rollout_dynamics(x0, torch.zeros(8, 1)), torch.zeros(8, 1))
+    assert abs(cost0.item() - float(z["ctrlb_cost0"])) / float(z["ctrlb_cost0"]) < 1e-4
+    with pytest.raises(NotImplementedError):
+        MPCController(m, 8, 0.02, mpc["Q_diag"], 0.01, optimizer_type="LBFGS").compute_control(z["ctrl_x"][0])
+    with pytest.raises(ValueError):
+        MPCController(m, 8, 0.02, mpc["Q_diag"], 0.01, optimizer_type="SGD").compute_control(z["ctrl_x"][0])
+
+
+def test_mpc_controller_canonical_control_cfg3():
+    """BASELINE config 3 (B=1 form): control() cold start, then warm start from the shifted plan."""
+    from phnn_mpc_b200.dropin.mpc_controller_canonical import create_mpc_controller
+    z, m = _model("canonical", "canonical")
+    cfg = yaml.safe_load(open(os.path.join(CONFIGS, "pole_stabilization.yaml")))
+    c = create_mpc_controller(m, cfg)
+    assert c.horizon == 10 and c.optimizer_steps == 50 and c.u_max == 30.0
+    lr = cfg["mpc"]["learning_rate"]
+    for i, s in enumerate(z["ctrl_x"]):
+        u1, info1 = c.control(s)
+        assert u1.shape == (1,) and info1["u_sequence"].shape == (10, 1) and info1["solve_time"] > 0
+        assert np.abs(info1["u_sequence"] - z["ctrl_seq"][i, 0]).max() < 0.05 * lr
+        assert rel_err(np.array(info1["optimization"]["costs"]), z["ctrl_costs"][i, 0]) < 1e-4
+        assert info1["optimization"]["num_steps"] == 50
+        assert abs(info1["optimization"]["final_cost"] - z["ctrl_costs"][i, 0].min()) <= 1e-4 * abs(z["ctrl_costs"][i, 0].min())
+        u2, info2 = c.control(s + 0.01, z["ctrl_seq"][i, 0])          # warm start from the golden plan
+        assert np.abs(info2["u_sequence"] - z["ctrl_seq"][i, 1]).max() < 0.05 * lr
+        assert abs(u2[0] - z["ctrl_u"][i, 1, 0]) < 0.05 * lr
+    out = c.solve_batch(z["ctrl_x"], want_hist=True)                 # batched: same three cold solves, one launch
+    assert np.abs(out["U"].cpu().numpy() - z["ctrl_seq"][:, 0]).max() < 0.05 * lr
+
+
+def test_closed_loop_with_plant_short():
+    """drop-in controller in the reference driver's loop shape (simulator <-> controller), 5 steps:
+    stays finite and applies bounded controls (scripts/run_cartpole_mpc.py:91-182)."""
+    from phnn_mpc_b200.dropin.mpc_controller import MPCController
+    z, m = _model("phnn", "cartpole_h128")
+    c = MPCController(m, 20, 0.02, [10.0, 200.0, 1.0, 10.0], 0.01, [0, 0, 0, 0], -15.0, 15.0, lr=0.015,
+                      max_iterations=30)
+    state = np.array([0.0, 0.1, 0.0, 0.0])
+    for _ in range(5):
+        u = c.compute_control(state)
+        assert np.isfinite(u).all() and -15.0 <= u[0] <= 15.0
+        x, th, xd, thd = state
+        f = float(u[0])
+        tmp = (f + 0.05 * thd ** 2 * np.sin(th)) / 1.1
+        tha = (9.8 * np.sin(th) - np.cos(th) * tmp) / (0.5 * (4.0 / 3.0 - 0.1 * np.cos(th) ** 2 / 1.1))
+        xa = tmp - 0.05 * tha * np.cos(th) / 1.1
+        state = np.array([x + 0.02 * xd, th + 0.02 * thd, xd + 0.02 * xa, thd + 0.02 * tha])
+    assert np.isfinite(state).all()

@@ -117,12 +117,23 @@ def test_pendulum_anchor_rollouts(env):
 
 @pytest.mark.parametrize("integ", ["rk4", "euler"])
 def test_pendulum_cfg2_rollout(env, integ):
-    """BASELINE config 2 inputs (first 64 instances) against the reference's own rollout."""
+    """BASELINE config 2 inputs (first 64 instances), 100 chained steps, against the reference's
+    own rollout.  This horizon amplifies rounding: two FP32 evaluations that differ only in
+    summation order (reference vs the CPU FP32 oracle) are 7e-5 apart and the FP32 oracle is
+    1e-4 from its FP64 twin, so the bound vs the reference is 2e-4 here, and the kernel must
+    also be no further from FP64 than twice the CPU FP32 oracle is."""
+    from oracle.phnn_oracle import OracleModel
     ops, get = env
     z, sd, pk = get("pendulum")
     tr, en = ops.rollout(pk.handle, cu(z["cfg2_x0"]), cu(z["cfg2_U"]), 0.05, {"euler": 0, "rk4": 1}[integ], 1)
-    assert rel_err(tr.cpu().numpy(), z["cfg2_traj_" + integ]) < HORIZON_TOL
-    assert rel_err(en.cpu().numpy(), z["cfg2_en_" + integ]) < HORIZON_TOL
+    tr, en = tr.cpu().numpy(), en.cpu().numpy()
+    assert rel_err(tr, z["cfg2_traj_" + integ]) < 2e-4
+    assert rel_err(en, z["cfg2_en_" + integ]) < 2e-4
+    o64 = OracleModel(sd, "phnn", np.float64).rollout(z["cfg2_x0"], z["cfg2_U"], 0.05, integ)
+    o32 = OracleModel(sd, "phnn", np.float32).rollout(z["cfg2_x0"], z["cfg2_U"], 0.05, integ)
+    assert rel_err(tr, o64) < max(2 * rel_err(o32, o64), 5e-5)
+    # the first 10 steps are within the per-step tolerance
+    assert rel_err(tr[:, :11], z["cfg2_traj_" + integ][:, :11]) < STEP_TOL
 
 
 @pytest.mark.parametrize("name", list(KINDS))

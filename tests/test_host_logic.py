@@ -1,0 +1,161 @@
+"""CPU-only tests: host logic, the C-ABI library's exports, drop-in construction parity and the
+multi-process sharding path (gloo, world_size 2).  No CUDA compute is invoked here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CONFIGS, REPO, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    """libphnn_mpc.so loads and exports what include/phnn_mpc.h declares."""
+    from phnn_mpc_b200.build import build_library
+    lib = ctypes.CDLL(build_library())
+    header = open(os.path.join(REPO, "include", "phnn_mpc.h")).read()
+    declared = set(re.findall(r"\b(phnn_[a-z_]+)\s*\(", header))
+    declared -= {"phnn_model_desc", "phnn_cost_desc", "phnn_pack"}
+    assert len(declared) >= 11
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    from phnn_mpc_b200 import _lib
+    assert set(_lib.EXPORTS) <= declared
+    lib.phnn_version.restype = ctypes.c_int
+    assert lib.phnn_version() >= 100
+
+
+def test_argument_errors_without_gpu():
+    """bad arguments are rejected before any CUDA call; messages come from phnn_last_error()."""
+    from phnn_mpc_b200 import _lib
+    L = _lib.lib()
+    assert L.phnn_pack_create(None, 0, None) == _lib.E_ARG
+    assert b"null" in L.phnn_last_error()
+    d = _lib.ModelDesc()
+    d.m = 2
+    h = ctypes.c_void_p()
+    assert L.phnn_pack_create(ctypes.byref(d), 0, ctypes.byref(h)) == _lib.E_UNSUPPORTED
+    assert L.phnn_workspace_bytes(None, 10, 10, 0) == 0
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.E_UNSUPPORTED, "x")
+    with pytest.raises(ValueError):
+        _lib.check(_lib.E_INTEGRATOR, "x")
+
+
+def test_ops_refuse_cpu_tensors():
+    """no CPU fallback: the ops raise on host tensors instead of computing something else"""
+    from phnn_mpc_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        ops.forward(0, torch.zeros(2, 4), torch.zeros(2, 1))
+    with pytest.raises(ValueError, match="Unknown integrator"):
+        ops.integrator_id("midpoint")
+
+
+def test_dropin_init_matches_reference_seeding():
+    """torch.manual_seed(s); pHNN(cfg) yields the reference's weights bit for bit (the golden
+    fixtures store the state_dicts the reference produced with the same seeds)."""
+    from phnn_mpc_b200.dropin.pHNN import pHNN
+    from phnn_mpc_b200.dropin.pHNN_canonical import pHNN_Canonical
+    torch.manual_seed(0)
+    m = pHNN(os.path.join(CONFIGS, "cartpole_phnn.yaml"))
+    _, sd = load_golden("cartpole_h128")
+    assert sorted(m.state_dict()) == sorted(sd)
+    for k, v in sd.items():
+        assert np.array_equal(m.state_dict()[k].numpy(), v), k
+    torch.manual_seed(0)
+    c = pHNN_Canonical(os.path.join(CONFIGS, "cartpole_phnn.yaml"))
+    _, sdc = load_golden("canonical")
+    assert sorted(c.state_dict()) == sorted(sdc)
+    for k in ("H_net.net.0.weight", "H_net.net.2.weight", "H_net.net.4.bias", "J", "G"):
+        assert np.array_equal(c.state_dict()[k].numpy(), sdc[k]), k
+    c.load_state_dict({k: torch.from_numpy(v) for k, v in sdc.items()})      # reference checkpoints load
+    p = pHNN(os.path.join(CONFIGS, "pendulum_phnn.yaml"))
+    _, sdp = load_golden("pendulum")
+    p.load_state_dict({k: torch.from_numpy(v) for k, v in sdp.items()})
+    assert p.G_net is not None and not hasattr(p, "G_fixed")
+
+
+def test_dropin_surface_matches_reference_signatures():
+    import inspect
+    from phnn_mpc_b200.dropin import integrators, mpc_controller, mpc_controller_canonical
+    sig = inspect.signature(mpc_controller.MPCController.__init__)
+    assert list(sig.parameters)[1:] == ["phnn_model", "horizon", "dt", "Q", "R", "target_state", "u_min", "u_max",
+                                        "x_min", "x_max", "optimizer_type", "lr", "max_iterations"]
+    assert sig.parameters["lr"].default == 0.1 and sig.parameters["max_iterations"].default == 50
+    sig = inspect.signature(mpc_controller_canonical.MPCControllerCanonical.__init__)
+    assert list(sig.parameters)[1:] == ["model", "horizon", "dt", "Q", "R", "x_target", "u_min", "u_max",
+                                        "optimizer_steps", "learning_rate", "verbose"]
+    assert sig.parameters["u_min"].default == -10.0 and sig.parameters["horizon"].default == 20
+    for fn in ("euler_step", "rk4_step", "rk4_step_with_energy", "rollout_trajectory",
+               "rollout_trajectory_differentiable"):
+        assert callable(getattr(integrators, fn))
+    assert list(inspect.signature(integrators.rollout_trajectory_differentiable).parameters) == [
+        "model", "y0", "controls", "dt", "integrator", "return_energies"]
+    assert callable(mpc_controller.create_mpc_from_config) and callable(mpc_controller_canonical.create_mpc_controller)
+
+
+def test_controller_construction_and_host_cost():
+    from phnn_mpc_b200.dropin.pHNN import pHNN
+    from phnn_mpc_b200.dropin.mpc_controller import MPCController
+    torch.manual_seed(0)
+    m = pHNN(os.path.join(CONFIGS, "cartpole_phnn.yaml"))
+    c = MPCController(m, 20, 0.02, [10.0, 200.0, 1.0, 10.0], 0.01, [0, 0, 0, 0], -15.0, 15.0, lr=0.015,
+                      max_iterations=30)
+    assert c.horizon == 20 and c.u_min == -15.0 and c.max_iterations == 30 and c.model is m
+    states = torch.arange(12, dtype=torch.float32).reshape(3, 4) / 10
+    controls = torch.tensor([[1.0], [-2.0]])
+    expect = sum(float(s @ c.Q @ s) for s in states) + 0.01 * 5.0
+    assert abs(float(c.compute_cost(states, controls)) - expect) < 1e-4
+    bad = MPCController(m, 5, 0.02, [1.0] * 4, 0.1, optimizer_type="SGD")
+    with pytest.raises(ValueError):
+        bad._check_optimizer()
+    spec = c._spec()
+    assert spec.op_args()[3] is True and spec.Q.shape == (4, 4)
+    half = MPCController(m, 5, 0.02, [1.0] * 4, 0.1, u_min=-1.0)      # one bound only: no clamp (reference :180)
+    assert half._spec().op_args()[3] is False
+
+
+def test_shard_bounds_cover_batch():
+    from phnn_mpc_b200.distributed import shard_bounds
+    for B in (0, 1, 7, 64, 1000, 1048576):
+        for ws in (1, 2, 3, 8):
+            cuts = [shard_bounds(B, ws, r) for r in range(ws)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from phnn_mpc_b200.distributed import sharded_solve, shard_bounds
+dist.init_process_group("gloo")
+rank, ws = dist.get_rank(), dist.get_world_size()
+B = 37
+x0 = torch.arange(B * 4, dtype=torch.float32).reshape(B, 4)
+U0 = torch.arange(B * 5, dtype=torch.float32).reshape(B, 5, 1)
+def fake_solve(x, U):      # stands in for BatchedMPC.solve: any per-instance map
+    return {"U": U * 2 + x[:, :1, None], "u0": (U * 2 + x[:, :1, None])[:, 0], "best_cost": x.sum(1), "cost_hist": None}
+out = sharded_solve(fake_solve, x0, U0)
+ref = fake_solve(x0, U0)
+ok = all(torch.equal(out[k], ref[k]) for k in ("U", "u0", "best_cost"))
+print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+'''
+
+
+def test_sharded_solve_gloo_world2(tmp_path):
+    """N>1 path on CPU: two gloo ranks, contiguous shards, final all_gather equals the unsharded result."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29731", str(script), REPO]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("OK") == 2
