@@ -81,11 +81,12 @@ class PackedModel:
             d.m = int(sd["G"].shape[1])
             d.G = ptr("G")
             # src/mass_matrix.py:283-285 (float32 arithmetic) and src/pHNN_canonical.py:162
-            la, lc = torch.as_tensor(sd["M_net.log_a"]).float(), torch.as_tensor(sd["M_net.log_c"]).float()
+            la = torch.as_tensor(sd["M_net.log_a"]).detach().float()
+            lc = torch.as_tensor(sd["M_net.log_c"]).detach().float()
             d.mass_a = float(torch.exp(la) + 1e-3)
-            d.mass_b = float(torch.as_tensor(sd["M_net.b"]).float())
+            d.mass_b = float(torch.as_tensor(sd["M_net.b"]).detach().float())
             d.mass_c = float(torch.exp(lc) + 1e-3)
-            rd = torch.nn.functional.softplus(torch.as_tensor(sd["R_diag_raw"]).float()) + 1e-4
+            rd = torch.nn.functional.softplus(torch.as_tensor(sd["R_diag_raw"]).detach().float()) + 1e-4
             sd["__r_diag"] = rd
             d.r_diag = ptr("__r_diag")
         else:
