@@ -76,6 +76,13 @@ int phnn_pack_create(const phnn_model_desc *desc, int device, phnn_pack **out);
 int phnn_pack_destroy(phnn_pack *pack);
 int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
 
+/* Kernel selection knobs (no reference counterpart).
+ *   "tensor_mode"      0: FP32-FMA kernel only; 3 (default where built): tcgen05 tensor cores with
+ *                      3xTF32 error compensation (FP32-level accuracy); 1: plain TF32 (looser).
+ *   "tensor_min_batch" smallest B routed to the tcgen05 kernel (default 4096).                  */
+int phnn_pack_set_option(phnn_pack *pack, const char *key, long value);
+long phnn_pack_get_option(const phnn_pack *pack, const char *key);
+
 /* dx[B,n], H[B] = model(x[B,n], u[B,m])          pHNN.forward src/pHNN.py:52-100,
  *                                                pHNN_Canonical.forward src/pHNN_canonical.py:172-273 */
 int phnn_forward(const phnn_pack *pack, const float *x, const float *u, float *dx, float *H, long B,

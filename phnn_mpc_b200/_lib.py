@@ -58,6 +58,10 @@ def lib():
                                  ctypes.c_size_t, vp]
     L.phnn_mpc_solve.argtypes = [vp, ctypes.POINTER(CostDesc), vp, vp, vp, vp, ll, ci, cd, ci, cd, cd, cd, cd, ci, ci,
                                  vp, ctypes.c_size_t, vp]
+    L.phnn_pack_set_option.argtypes = [vp, ctypes.c_char_p, ll]
+    L.phnn_pack_set_option.restype = ci
+    L.phnn_pack_get_option.argtypes = [vp, ctypes.c_char_p]
+    L.phnn_pack_get_option.restype = ll
     L.phnn_ffma_probe.argtypes = [vp, ci, ci, vp, ctypes.POINTER(cd)]
     L.phnn_ffma_probe.restype = ci
     for f in ("phnn_pack_create", "phnn_pack_destroy", "phnn_pack_dims", "phnn_forward", "phnn_vjp", "phnn_rollout",
@@ -68,7 +72,8 @@ def lib():
 
 
 EXPORTS = ["phnn_last_error", "phnn_version", "phnn_pack_create", "phnn_pack_destroy", "phnn_pack_dims",
-           "phnn_forward", "phnn_vjp", "phnn_rollout", "phnn_workspace_bytes", "phnn_cost_grad", "phnn_mpc_solve", "phnn_ffma_probe"]
+           "phnn_forward", "phnn_vjp", "phnn_rollout", "phnn_workspace_bytes", "phnn_cost_grad", "phnn_mpc_solve", "phnn_ffma_probe",
+           "phnn_pack_set_option", "phnn_pack_get_option"]
 
 
 def check(rc, what):

@@ -3,6 +3,7 @@
 // every entry point either launches the sm_100a kernel or returns an error.
 #include "../../include/phnn_mpc.h"
 #include "phnn_kernel.cuh"
+#include "phnn_tc_kernel.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -15,8 +16,12 @@ using namespace phnn;
 struct phnn_pack {
     int abi_kind, mk, n, m, h;
     int device, num_sms;
+    int tc_mode;          // 0: FP32-FMA kernel only; 3: tcgen05 3xTF32 when eligible; 1: tcgen05 plain TF32
+    long tc_min_batch;    // smallest B routed to the tcgen05 kernel
     float* d_small;
     float* d_big;
+    unsigned char* d_wtc;
+    float* d_small_tc;
     size_t small_floats;
     KParams base;  // model constants filled in once
 };
@@ -54,6 +59,64 @@ extern "C" int phnn_version(void) { return 100; }
     X(MK_CANON, 4, 64) \
     X(MK_CANON, 4, 128) \
     X(MK_CANON, 4, 256)
+
+// shapes with a tcgen05 instantiation (cart-pole pHNN, fixed G)
+#define PHNN_TC_SHAPES(X) \
+    X(MK_PHNN, 4, 128)    \
+    X(MK_PHNN, 4, 256)
+
+static bool has_tc_shape(int mk, int n, int h) {
+#define X(MK, NS, HID) \
+    if (mk == MK && n == NS && h == HID) return true;
+    PHNN_TC_SHAPES(X)
+#undef X
+    return false;
+}
+
+static float tf32_round_host(float x) {  // cvt.rna.tf32.f32
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;
+    u &= 0xFFFFE000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
+
+// pre-swizzled K-blocks: [P: W2 | W2^T][kb][hi|lo][h rows x 128 B]
+static void fill_tc_big(const phnn_model_desc* d, std::vector<unsigned char>& out) {
+    const int h = d->h, nkb = h / 32;
+    const size_t tile = (size_t)h * 128;
+    out.assign((size_t)2 * nkb * 2 * tile, 0);
+    for (int P = 0; P < 2; ++P)
+        for (int kb = 0; kb < nkb; ++kb)
+            for (int n = 0; n < h; ++n)
+                for (int c = 0; c < 32; ++c) {
+                    const int K = kb * 32 + c;
+                    const float val = (P == 0) ? d->W2[(size_t)n * h + K] : d->W2[(size_t)K * h + n];
+                    const float hi = tf32_round_host(val), lo = val - hi;
+                    const size_t base = ((size_t)(P * nkb + kb) * 2) * tile;
+                    memcpy(&out[base + sw128_off(n, c)], &hi, 4);
+                    memcpy(&out[base + tile + sw128_off(n, c)], &lo, 4);
+                }
+}
+
+static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
+    const int h = d->h, n = d->n, nn = n * n;
+    s.assign((size_t)h * (8 + 4 + nn), 0.f);
+    float* rA = s.data();
+    float* rB = rA + (size_t)h * 8;
+    float* rC = rB + (size_t)h * 4;
+    for (int k = 0; k < h; ++k) {
+        for (int i = 0; i < n; ++i) rA[k * 8 + i] = d->W1[k * n + i];
+        rA[k * 8 + 4] = d->b1[k];
+        rA[k * 8 + 5] = d->b2[k];
+        rA[k * 8 + 6] = d->W3[k];
+        rA[k * 8 + 7] = d->br1[k];
+        for (int i = 0; i < n; ++i) rB[k * 4 + i] = d->Wr1[k * n + i];
+        for (int c = 0; c < nn; ++c) rC[k * nn + c] = d->Wr2[(size_t)c * h + k];
+    }
+}
 
 template <class SH>
 static void fill_small(const phnn_model_desc* d, std::vector<float>& s) {
@@ -131,10 +194,24 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
     if (e == cudaSuccess) e = cudaMalloc(&pk->d_big, big.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(pk->d_small, small.data(), small.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(pk->d_big, big.data(), big.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && has_tc_shape(mk, n, h)) {
+        std::vector<unsigned char> wtc;
+        std::vector<float> stc;
+        fill_tc_big(d, wtc);
+        fill_tc_small(d, stc);
+        e = cudaMalloc(&pk->d_wtc, wtc.size());
+        if (e == cudaSuccess) e = cudaMalloc(&pk->d_small_tc, stc.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(pk->d_wtc, wtc.data(), wtc.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(pk->d_small_tc, stc.data(), stc.size() * sizeof(float), cudaMemcpyHostToDevice);
+        pk->tc_mode = 3;
+        pk->tc_min_batch = 4096;
+    }
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         cudaFree(pk->d_small);
         cudaFree(pk->d_big);
+        cudaFree(pk->d_wtc);
+        cudaFree(pk->d_small_tc);
         delete pk;
         return cuda_fail(e, "phnn_pack_create");
     }
@@ -142,6 +219,8 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
     KParams& P = pk->base;
     P.wsmall = pk->d_small;
     P.wbig = pk->d_big;
+    P.wtc = pk->d_wtc;
+    P.wsmall_tc = pk->d_small_tc;
     for (int a = 0; a < n; ++a)
         for (int b = 0; b < n; ++b)
             P.Jm[a * n + b] = (mk == MK_CANON) ? d->J[a * n + b] : (d->J[a * n + b] - d->J[b * n + a]);
@@ -163,8 +242,32 @@ extern "C" int phnn_pack_destroy(phnn_pack* pk) {
     if (!pk) return 0;
     cudaFree(pk->d_small);
     cudaFree(pk->d_big);
+    cudaFree(pk->d_wtc);
+    cudaFree(pk->d_small_tc);
     delete pk;
     return 0;
+}
+
+extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) {
+    if (!pk || !key) return fail(PHNN_E_ARG, "phnn_pack_set_option: null argument");
+    if (!strcmp(key, "tensor_mode")) {
+        if (value != 0 && value != 1 && value != 3) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1 or 3");
+        if (value != 0 && !pk->d_wtc) return fail(PHNN_E_UNSUPPORTED, "no tcgen05 kernel for this model shape");
+        pk->tc_mode = (int)value;
+        return 0;
+    }
+    if (!strcmp(key, "tensor_min_batch")) {
+        pk->tc_min_batch = value;
+        return 0;
+    }
+    return fail(PHNN_E_ARG, "unknown option %s", key);
+}
+
+extern "C" long phnn_pack_get_option(const phnn_pack* pk, const char* key) {
+    if (!pk || !key) return -1;
+    if (!strcmp(key, "tensor_mode")) return pk->tc_mode;
+    if (!strcmp(key, "tensor_min_batch")) return pk->tc_min_batch;
+    return -1;
 }
 
 extern "C" int phnn_pack_dims(const phnn_pack* pk, int* kind, int* n, int* m, int* h) {
@@ -193,12 +296,34 @@ static int launch_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
     return 0;
 }
 
+template <class SH>
+static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
+    const long long tiles = (P.B + SH::TM - 1) / SH::TM;
+    auto kern = phnn_tc_kernel<SH::MK, SH::NS, SH::HID>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
+    P.tc_split = pk->tc_mode == 1 ? 1 : 3;
+    P.ng = 1;
+    kern<<<(unsigned)tiles, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int launch(const phnn_pack* pk, KParams& P, void* stream) {
     if (P.B <= 0) return 0;
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != pk->device) CUDA_TRY(cudaSetDevice(pk->device));
     int rc = fail(PHNN_E_UNSUPPORTED, "no kernel instantiation");
+    // tcgen05 path only when batch x hidden width make the layer products a real dense contraction
+    // (phnn_vjp carries no workspace for the tcgen05 kernel's activation stash: it stays on the FP32 kernel)
+    if (pk->tc_mode != 0 && pk->d_wtc && P.B >= pk->tc_min_batch && P.mode != MODE_VJP) {
+#define X(MK, NS, HID) \
+    if (pk->mk == MK && pk->n == NS && pk->h == HID) rc = launch_tc_shape<TcShape<MK, NS, HID>>(pk, P, (cudaStream_t)stream);
+        PHNN_TC_SHAPES(X)
+#undef X
+        if (prev != pk->device) cudaSetDevice(prev);
+        return rc;
+    }
 #define X(MK, NS, HID) \
     if (pk->mk == MK && pk->n == NS && pk->h == HID) rc = launch_shape<Shape<MK, NS, HID>>(pk, P, (cudaStream_t)stream);
     PHNN_SHAPES(X)
@@ -280,8 +405,9 @@ extern "C" int phnn_rollout(const phnn_pack* pk, const float* x0, const float* U
 
 extern "C" size_t phnn_workspace_bytes(const phnn_pack* pk, long B, int T, int integrator) {
     if (!pk || B <= 0 || T <= 0) return 0;
-    const size_t groups = ((size_t)B + GI - 1) / GI;
-    return groups * ws_floats_per_group(pk->n, T, integrator == PHNN_RK4 ? 4 : 1) * sizeof(float);
+    // sized for 128-instance tiles (the tcgen05 kernel); a superset of what 32-instance tiles need
+    const size_t tiles = ((size_t)B + 127) / 128;
+    return tiles * ws_floats_per_tile(pk->n, T, integrator == PHNN_RK4 ? 4 : 1, 128, pk->h) * sizeof(float);
 }
 
 extern "C" int phnn_cost_grad(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, const float* U,

@@ -80,6 +80,9 @@ struct KParams {
     // packed weights (HBM)
     const float* wsmall;
     const float* wbig;  // [W2^T | W2], each [HID][HID]
+    const unsigned char* wtc;  // tcgen05 path: pre-swizzled hi/lo K-blocks of W2 and W2^T
+    const float* wsmall_tc;    // tcgen05 path: per-hidden-unit records of the small layers
+    int tc_split;              // 3 = 3xTF32 (FP32-level accuracy), 1 = plain TF32
     // model constants
     float Jm[16];  // MK 0/1: J - J^T ; MK 2: the canonical J buffer
     float Gv[4];
@@ -111,9 +114,11 @@ struct KParams {
     float* ws;         // workspace
 };
 
-// floats of workspace per group of 32 instances
-__host__ __device__ inline size_t ws_floats_per_group(int NS, int T, int S) {
-    return (size_t)GI * ((size_t)T * S * NS + 3 * (size_t)T);
+// floats of workspace per tile of TW instances: stage states [T*S][NS][TW], Adam m, v and best
+// controls [T][TW] (lane-interleaved so the accesses of a warp coalesce)
+// (+ `extra` floats per instance: the tcgen05 kernel stashes one hidden-layer activation there)
+__host__ __device__ inline size_t ws_floats_per_tile(int NS, int T, int S, int TW, int extra = 0) {
+    return (size_t)TW * ((size_t)T * S * NS + 3 * (size_t)T + (size_t)extra);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -213,10 +218,20 @@ __device__ __forceinline__ void lane8_reduce(float* v, int lo) {
 // Dynamic shared memory of the CTA.  Everything is addressed as (this symbol + offset) so the
 // compiler emits shared-space LDS/STS with 32-bit addresses instead of generic LD/ST (the first
 // ncu capture showed LD.E.128 in the product loop and ~20% long-scoreboard stalls on them).
-extern __shared__ __align__(128) unsigned char phnn_smem[];
+extern __shared__ __align__(1024) unsigned char phnn_smem[];
+
+template <class SH> struct Ctx;
+template <class SH>
+__device__ void eval_fwd(Ctx<SH>& c, const KParams& p, const float (&y)[SH::NS], float u, float (&f)[SH::NS], float& Hval);
+template <class SH>
+__device__ void eval_vjp(Ctx<SH>& c, const KParams& p, const float (&y)[SH::NS], float u, const float (&v)[SH::NS],
+                         float (&xbar)[SH::NS], float& ubar);
 
 template <class SH>
 struct Ctx {
+    static constexpr int NS = SH::NS;
+    static constexpr int TW = GI;  // instances per workspace tile
+    static constexpr int WS_EXTRA = 0;
     uint32_t goff;  // float offset of this group's region
     int lane, li, lo, wg, barid, wcol, chunk;
     uint32_t tile;  // ring tiles consumed so far
@@ -240,6 +255,13 @@ struct Ctx {
     // hidden unit handled in micro-tile column o
     __device__ __forceinline__ int kown(int o) const { return wcol + ((o >> 2) << 5) + (o & 3); }
     __device__ __forceinline__ float* row_own(float* buf, int k) const { return buf + k * GI + (chunk << 3); }
+    __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
+        phnn::eval_fwd(*this, p, y, u, f, H);
+    }
+    __device__ __forceinline__ void eval_vjp(const KParams& p, const float (&y)[NS], float u, const float (&v)[NS],
+                                             float (&xbar)[NS], float& ubar) {
+        phnn::eval_vjp(*this, p, y, u, v, xbar, ubar);
+    }
 };
 
 // acc[r][o] += sum_k lhs[k][8*li + r] * W[k][kown(o)] over one full sweep of HID rows taken
@@ -900,6 +922,227 @@ __device__ __forceinline__ float clampu(const KParams& p, float u) {
 }
 
 // ---------------------------------------------------------------------------------------
+// One job for one instance, shared by the FP32-FMA and the tcgen05 kernels.  ENG supplies the
+// collective dynamics evaluations (eval_fwd / eval_vjp run by all threads of a tile together),
+// gbar() (a barrier among the threads that co-own an instance) and `store` (exactly one of the
+// co-owning threads performs the global stores).  tile/slot locate the instance and its
+// lane-interleaved workspace.
+// ---------------------------------------------------------------------------------------
+template <class ENG>
+__device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long long tile, const int slot,
+                                        const int n_outer) {
+    constexpr int NS = ENG::NS, TW = ENG::TW;
+    const long long b = tile * TW + slot;  // my instance
+    const bool valid = b < p.B;
+    const bool st = valid && c.store;
+    const int T = p.T, S = p.S;
+    const int E = T * S;
+
+    float x0[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x0[i] = valid ? p.x0[b * NS + i] : 0.f;
+
+    if (p.mode == MODE_FORWARD) {
+        const float u = valid ? p.uin[b] : 0.f;
+        float f[NS], Hv;
+        c.eval_fwd(p, x0, u, f, Hv);
+        if (st) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = f[i];
+            p.out1[b] = Hv;
+        }
+        return;
+    }
+    if (p.mode == MODE_VJP) {
+        const float u = valid ? p.uin[b] : 0.f;
+        float v[NS], xb[NS], ub;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) v[i] = valid ? p.vin[b * NS + i] : 0.f;
+        c.eval_vjp(p, x0, u, v, xb, ub);
+        if (st) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = xb[i];
+            p.out1[b] = ub;
+        }
+        return;
+    }
+
+    // workspace of this group: stage states [E][NS][32], Adam m/v and best controls [T][32]
+    float* wsg = p.ws ? p.ws + (size_t)tile * ws_floats_per_tile(NS, T, S, TW, ENG::WS_EXTRA) : nullptr;
+    float* ckpt = wsg;
+    float* adam_m = wsg ? wsg + (size_t)E * NS * TW : nullptr;
+    float* adam_v = adam_m ? adam_m + (size_t)T * TW : nullptr;
+    float* ubest = adam_v ? adam_v + (size_t)T * TW : nullptr;
+    const bool solve = (p.mode == MODE_SOLVE);
+    const bool need_adj = solve || (p.mode == MODE_COSTGRAD && p.want_grad);
+    const float* Uread = solve ? p.U : p.uin;
+    float* traj = (p.mode == MODE_SOLVE) ? nullptr : p.out0;
+
+    if (solve && st) {
+        for (int t = 0; t < T; ++t) {
+            adam_m[t * TW + slot] = 0.f;
+            adam_v[t * TW + slot] = 0.f;
+            ubest[t * TW + slot] = clampu(p, p.U[b * T + t]);
+        }
+    }
+    float best = __int_as_float(0x7f800000);
+
+#pragma unroll 1
+    for (int it = 1; it <= n_outer; ++it) {
+        // ---------------- forward sweep ----------------
+        float x[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) x[i] = x0[i];
+        float cost = 0.f;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            const float uraw = valid ? __ldcg(Uread + b * T + t) : 0.f;
+            const float u = clampu(p, uraw);
+            if (p.mode != MODE_ROLLOUT) {
+                cost += state_cost<NS>(p, x, nullptr);
+                cost = fmaf(p.Rw * u, u, cost);
+            }
+            if (traj && st) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) traj[(b * (T + 1) + t) * NS + i] = x[i];
+            }
+            float k[NS], ksum[NS], ys[NS], Hv;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { ys[i] = x[i]; ksum[i] = 0.f; }
+#pragma unroll 1
+            for (int s = 0; s < S; ++s) {
+                if (need_adj && st) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) ckpt[((size_t)(t * S + s) * NS + i) * TW + slot] = ys[i];
+                }
+                c.eval_fwd(p, ys, u, k, Hv);
+                if (s == 0 && p.mode == MODE_ROLLOUT && p.out1 && st) {
+                    // H(y_t): differentiable-rollout ordering puts it at index t+1 (and 0)
+                    if (p.energy_mode == 1) {
+                        p.out1[b * (T + 1) + t + 1] = Hv;
+                        if (t == 0) p.out1[b * (T + 1)] = Hv;
+                    } else {
+                        p.out1[b * (T + 1) + t] = Hv;
+                    }
+                }
+                if (S == 1) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) x[i] = fmaf(p.dt, k[i], x[i]);
+                } else {
+                    // classical RK4, u held over the step (src/integrators.py:66-82)
+                    if (s == 0) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) { ksum[i] = k[i]; ys[i] = fmaf(p.dt2, k[i], x[i]); }
+                    } else if (s == 1) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) { ksum[i] = fmaf(2.f, k[i], ksum[i]); ys[i] = fmaf(p.dt2, k[i], x[i]); }
+                    } else if (s == 2) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) { ksum[i] = fmaf(2.f, k[i], ksum[i]); ys[i] = fmaf(p.dt, k[i], x[i]); }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) x[i] = fmaf(p.dt6, ksum[i] + k[i], x[i]);
+                    }
+                }
+            }
+        }
+        if (p.mode != MODE_ROLLOUT) cost += state_cost<NS>(p, x, nullptr);
+        if (traj && st) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) traj[(b * (T + 1) + T) * NS + i] = x[i];
+        }
+        if (p.mode == MODE_ROLLOUT) {
+            if (p.energy_mode == 2) {
+                float k[NS], Hv;
+                c.eval_fwd(p, x, 0.f, k, Hv);
+                if (p.out1 && st) p.out1[b * (T + 1) + T] = Hv;
+            }
+            return;
+        }
+        if (p.mode == MODE_COSTGRAD && st) p.cost[b] = cost;
+        if (solve && st && p.cost_hist) p.cost_hist[(size_t)(it - 1) * p.B + b] = cost;
+        if (!need_adj) return;
+
+        // ---------------- reverse sweep (discrete adjoint) ----------------
+        const bool improved = cost < best;
+        if (improved) best = cost;
+        float step_size = 0.f, bc2s = 1.f;
+        if (solve) {
+            // torch.optim.Adam (single-tensor path): bias corrections in double
+            const double bc1 = 1.0 - pow(p.beta1, (double)it);
+            const double bc2 = 1.0 - pow(p.beta2, (double)it);
+            step_size = (float)(p.lr / bc1);
+            bc2s = (float)sqrt(bc2);
+        }
+        const float w1 = (float)(1.0 - p.beta1), b2f = (float)p.beta2, w2 = (float)(1.0 - p.beta2), epsf = (float)p.eps;
+
+        float lam[NS];
+        state_cost<NS>(p, x, lam);
+#pragma unroll 1
+        for (int t = T - 1; t >= 0; --t) {
+            const float uraw = valid ? __ldcg(Uread + b * T + t) : 0.f;
+            const float u = clampu(p, uraw);
+            float ubsum = 0.f, y[NS], xb[NS], ub, kb[NS], ysum[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ysum[i] = 0.f;
+#pragma unroll 1
+            for (int s = S - 1; s >= 0; --s) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i)
+                    y[i] = valid ? __ldcg(ckpt + ((size_t)(t * S + s) * NS + i) * TW + slot) : 0.f;
+                if (S == 1) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) kb[i] = p.dt * lam[i];
+                } else if (s == 3) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) kb[i] = p.dt6 * lam[i];
+                } else if (s == 2) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt * xb[i]);
+                } else if (s == 1) {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt2 * xb[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt6, lam[i], p.dt2 * xb[i]);
+                }
+                c.eval_vjp(p, y, u, kb, xb, ub);
+                ubsum += ub;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) ysum[i] += xb[i];
+            }
+            // y now holds x_t (stage 0 state)
+            float gl[NS];
+            state_cost<NS>(p, y, gl);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) lam[i] += ysum[i] + gl[i];
+            float g = fmaf(2.f * p.Rw, u, ubsum);
+            if (p.has_ub && !(uraw >= p.umin && uraw <= p.umax)) g = 0.f;  // clamp is inside the graph
+            if (p.mode == MODE_COSTGRAD) {
+                if (st) p.dJdU[b * T + t] = g;
+            } else if (st) {
+                if (improved) ubest[t * TW + slot] = u;
+                float m = adam_m[t * TW + slot], vv = adam_v[t * TW + slot];
+                m = m + w1 * (g - m);
+                vv = vv * b2f + w2 * g * g;
+                adam_m[t * TW + slot] = m;
+                adam_v[t * TW + slot] = vv;
+                const float den = sqrtf(vv) / bc2s + epsf;
+                p.U[b * T + t] = uraw + (-step_size * m) / den;
+            }
+        }
+        // the storing warp's update of U[.,0] must be visible to the group's other warps before
+        // they re-read it at the top of the next forward sweep
+        c.gbar();
+    }
+    if (solve && st) {
+        for (int t = 0; t < T; ++t)
+            p.U[b * T + t] = (p.return_mode == 0) ? clampu(p, __ldcg(p.U + b * T + t)) : ubest[t * TW + slot];
+        if (p.cost) p.cost[b] = best;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
 template <int MK, int NS, int HID>
@@ -979,214 +1222,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) phnn_kernel(const __grid_const
     c.goff = SH::SMALL + SH::RING + grp * SH::G_FLOATS;
     mbar_wait(&bars[2 * NST], 0);  // small weights landed
 
-    const long long gg = (long long)blockIdx.x * p.ng + grp;  // global group index
-    const long long b = gg * GI + lane;                       // my instance
-    const bool valid = b < p.B;
-    const bool st = valid && c.store;
-    const int T = p.T, S = p.S;
-
-    float x0[NS];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) x0[i] = valid ? p.x0[b * NS + i] : 0.f;
-
-    if (p.mode == MODE_FORWARD) {
-        const float u = valid ? p.uin[b] : 0.f;
-        float f[NS], Hv;
-        eval_fwd(c, p, x0, u, f, Hv);
-        if (st) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = f[i];
-            p.out1[b] = Hv;
-        }
-        return;
-    }
-    if (p.mode == MODE_VJP) {
-        const float u = valid ? p.uin[b] : 0.f;
-        float v[NS], xb[NS], ub;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) v[i] = valid ? p.vin[b * NS + i] : 0.f;
-        eval_vjp(c, p, x0, u, v, xb, ub);
-        if (st) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = xb[i];
-            p.out1[b] = ub;
-        }
-        return;
-    }
-
-    // workspace of this group: stage states [E][NS][32], Adam m/v and best controls [T][32]
-    float* wsg = p.ws ? p.ws + (size_t)gg * ws_floats_per_group(NS, T, S) : nullptr;
-    float* ckpt = wsg;
-    float* adam_m = wsg ? wsg + (size_t)E * NS * GI : nullptr;
-    float* adam_v = adam_m ? adam_m + (size_t)T * GI : nullptr;
-    float* ubest = adam_v ? adam_v + (size_t)T * GI : nullptr;
-    const bool solve = (p.mode == MODE_SOLVE);
-    const bool need_adj = solve || (p.mode == MODE_COSTGRAD && p.want_grad);
-    const float* Uread = solve ? p.U : p.uin;
-    float* traj = (p.mode == MODE_SOLVE) ? nullptr : p.out0;
-
-    if (solve && st) {
-        for (int t = 0; t < T; ++t) {
-            adam_m[t * GI + lane] = 0.f;
-            adam_v[t * GI + lane] = 0.f;
-            ubest[t * GI + lane] = clampu(p, p.U[b * T + t]);
-        }
-    }
-    float best = __int_as_float(0x7f800000);
-
-#pragma unroll 1
-    for (int it = 1; it <= n_outer; ++it) {
-        // ---------------- forward sweep ----------------
-        float x[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) x[i] = x0[i];
-        float cost = 0.f;
-#pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-            const float uraw = valid ? __ldcg(Uread + b * T + t) : 0.f;
-            const float u = clampu(p, uraw);
-            if (p.mode != MODE_ROLLOUT) {
-                cost += state_cost<NS>(p, x, nullptr);
-                cost = fmaf(p.Rw * u, u, cost);
-            }
-            if (traj && st) {
-#pragma unroll
-                for (int i = 0; i < NS; ++i) traj[(b * (T + 1) + t) * NS + i] = x[i];
-            }
-            float k[NS], ksum[NS], ys[NS], Hv;
-#pragma unroll
-            for (int i = 0; i < NS; ++i) { ys[i] = x[i]; ksum[i] = 0.f; }
-#pragma unroll 1
-            for (int s = 0; s < S; ++s) {
-                if (need_adj && st) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) ckpt[((size_t)(t * S + s) * NS + i) * GI + lane] = ys[i];
-                }
-                eval_fwd(c, p, ys, u, k, Hv);
-                if (s == 0 && p.mode == MODE_ROLLOUT && p.out1 && st) {
-                    // H(y_t): differentiable-rollout ordering puts it at index t+1 (and 0)
-                    if (p.energy_mode == 1) {
-                        p.out1[b * (T + 1) + t + 1] = Hv;
-                        if (t == 0) p.out1[b * (T + 1)] = Hv;
-                    } else {
-                        p.out1[b * (T + 1) + t] = Hv;
-                    }
-                }
-                if (S == 1) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) x[i] = fmaf(p.dt, k[i], x[i]);
-                } else {
-                    // classical RK4, u held over the step (src/integrators.py:66-82)
-                    if (s == 0) {
-#pragma unroll
-                        for (int i = 0; i < NS; ++i) { ksum[i] = k[i]; ys[i] = fmaf(p.dt2, k[i], x[i]); }
-                    } else if (s == 1) {
-#pragma unroll
-                        for (int i = 0; i < NS; ++i) { ksum[i] = fmaf(2.f, k[i], ksum[i]); ys[i] = fmaf(p.dt2, k[i], x[i]); }
-                    } else if (s == 2) {
-#pragma unroll
-                        for (int i = 0; i < NS; ++i) { ksum[i] = fmaf(2.f, k[i], ksum[i]); ys[i] = fmaf(p.dt, k[i], x[i]); }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NS; ++i) x[i] = fmaf(p.dt6, ksum[i] + k[i], x[i]);
-                    }
-                }
-            }
-        }
-        if (p.mode != MODE_ROLLOUT) cost += state_cost<NS>(p, x, nullptr);
-        if (traj && st) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) traj[(b * (T + 1) + T) * NS + i] = x[i];
-        }
-        if (p.mode == MODE_ROLLOUT) {
-            if (p.energy_mode == 2) {
-                float k[NS], Hv;
-                eval_fwd(c, p, x, 0.f, k, Hv);
-                if (p.out1 && st) p.out1[b * (T + 1) + T] = Hv;
-            }
-            return;
-        }
-        if (p.mode == MODE_COSTGRAD && st) p.cost[b] = cost;
-        if (solve && st && p.cost_hist) p.cost_hist[(size_t)(it - 1) * p.B + b] = cost;
-        if (!need_adj) return;
-
-        // ---------------- reverse sweep (discrete adjoint) ----------------
-        const bool improved = cost < best;
-        if (improved) best = cost;
-        float step_size = 0.f, bc2s = 1.f;
-        if (solve) {
-            // torch.optim.Adam (single-tensor path): bias corrections in double
-            const double bc1 = 1.0 - pow(p.beta1, (double)it);
-            const double bc2 = 1.0 - pow(p.beta2, (double)it);
-            step_size = (float)(p.lr / bc1);
-            bc2s = (float)sqrt(bc2);
-        }
-        const float w1 = (float)(1.0 - p.beta1), b2f = (float)p.beta2, w2 = (float)(1.0 - p.beta2), epsf = (float)p.eps;
-
-        float lam[NS];
-        state_cost<NS>(p, x, lam);
-#pragma unroll 1
-        for (int t = T - 1; t >= 0; --t) {
-            const float uraw = valid ? __ldcg(Uread + b * T + t) : 0.f;
-            const float u = clampu(p, uraw);
-            float ubsum = 0.f, y[NS], xb[NS], ub, kb[NS], ysum[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) ysum[i] = 0.f;
-#pragma unroll 1
-            for (int s = S - 1; s >= 0; --s) {
-#pragma unroll
-                for (int i = 0; i < NS; ++i)
-                    y[i] = valid ? __ldcg(ckpt + ((size_t)(t * S + s) * NS + i) * GI + lane) : 0.f;
-                if (S == 1) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = p.dt * lam[i];
-                } else if (s == 3) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = p.dt6 * lam[i];
-                } else if (s == 2) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt * xb[i]);
-                } else if (s == 1) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt2 * xb[i]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt6, lam[i], p.dt2 * xb[i]);
-                }
-                eval_vjp(c, p, y, u, kb, xb, ub);
-                ubsum += ub;
-#pragma unroll
-                for (int i = 0; i < NS; ++i) ysum[i] += xb[i];
-            }
-            // y now holds x_t (stage 0 state)
-            float gl[NS];
-            state_cost<NS>(p, y, gl);
-#pragma unroll
-            for (int i = 0; i < NS; ++i) lam[i] += ysum[i] + gl[i];
-            float g = fmaf(2.f * p.Rw, u, ubsum);
-            if (p.has_ub && !(uraw >= p.umin && uraw <= p.umax)) g = 0.f;  // clamp is inside the graph
-            if (p.mode == MODE_COSTGRAD) {
-                if (st) p.dJdU[b * T + t] = g;
-            } else if (st) {
-                if (improved) ubest[t * GI + lane] = u;
-                float m = adam_m[t * GI + lane], vv = adam_v[t * GI + lane];
-                m = m + w1 * (g - m);
-                vv = vv * b2f + w2 * g * g;
-                adam_m[t * GI + lane] = m;
-                adam_v[t * GI + lane] = vv;
-                const float den = sqrtf(vv) / bc2s + epsf;
-                p.U[b * T + t] = uraw + (-step_size * m) / den;
-            }
-        }
-        // the storing warp's update of U[.,0] must be visible to the group's other warps before
-        // they re-read it at the top of the next forward sweep
-        c.gbar();
-    }
-    if (solve && st) {
-        for (int t = 0; t < T; ++t)
-            p.U[b * T + t] = (p.return_mode == 0) ? clampu(p, __ldcg(p.U + b * T + t)) : ubest[t * GI + lane];
-        if (p.cost) p.cost[b] = best;
-    }
+    run_job(c, p, (long long)blockIdx.x * p.ng + grp, lane, n_outer);
 }
 
 }  // namespace phnn

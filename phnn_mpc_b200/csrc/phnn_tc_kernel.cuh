@@ -1,0 +1,638 @@
+// phnn_tc_kernel.cuh -- tcgen05 / TMEM version of the fused pHNN-MPC kernel (sm_100a).
+//
+// Same jobs and same per-instance arithmetic as phnn_kernel.cuh (run_job is shared); only the
+// two h x h layers of H_net -- the dense contraction [128 instances, h] x [h, h] that carries
+// >90 % of the FLOPs -- move to the 5th-generation tensor cores:
+//
+//   * tile = 128 instances = UMMA M.  Accumulators (z2 / g1, then dz2 / dg1 in the adjoint)
+//     live in TMEM: 2 x h fp32 columns, all 512 columns at h = 256.
+//   * operand A (activations) is produced by the element threads, 32 hidden units (one
+//     128-byte swizzle row of tf32) at a time, straight into a 2-slot shared-memory ring in
+//     the K-major SWIZZLE_128B layout the UMMA descriptor expects; the MMA of one product
+//     overlaps with the elementwise work that produces the next K-block, so layer outputs
+//     never exist as whole [128, h] matrices.
+//   * operand B (W2 for z2/dz2, W2^T for g1/dg1) is pre-swizzled on the host and streamed from
+//     L2 by a producer warp with cp.async.bulk into a 3-entry ring.
+//   * FP32 accuracy on TF32 tensor cores by error compensation (3xTF32): x = hi + lo with
+//     hi = cvt.rna.tf32(x); A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo, accumulated in FP32 in TMEM
+//     (measured 2e-6 relative on a K=256 product vs 6e-7 for an FP32 FMA chain and 3e-4 for
+//     plain TF32; tools/tc_probe.cu).  split = 1 selects plain TF32 (looser, stated tolerance).
+//   * thread = instance: element thread (row, half) owns 16 of every 32 hidden units of one
+//     instance (tcgen05.ld 32x32b gives a thread its own TMEM lane), so every reduction over
+//     the hidden dimension is a private register loop; the two halves of an instance meet in
+//     one small shared-memory exchange per reduction.
+//
+// Roles: warps 0-7 element threads (256), warp 8 MMA issuer (one lane), warp 9 weight producer.
+#pragma once
+#include "phnn_kernel.cuh"
+
+namespace phnn {
+
+template <int MK_, int NS_, int HID_>
+struct TcShape {
+    static_assert(MK_ == MK_PHNN && NS_ == 4, "tensor-core path: cart-pole pHNN (fixed G, n = 4)");
+    static constexpr int MK = MK_, NS = NS_, HID = HID_, NN = NS * NS;
+    static constexpr int TM = 128;         // instances per tile (UMMA M)
+    static constexpr int NKB = HID / 32;   // K-blocks of 32 tf32 (one 128-byte swizzle row)
+    static constexpr int A_TILE = TM * 128;   // bytes of one A K-block (hi or lo)
+    static constexpr int B_TILE = HID * 128;  // bytes of one B K-block (hi or lo)
+    static constexpr int NBE = 3;             // B ring entries
+    static constexpr int TMEM_COLS = (2 * HID <= 32) ? 32 : (2 * HID <= 64) ? 64 : (2 * HID <= 128) ? 128 : (2 * HID <= 256) ? 256 : 512;
+    // small weights (floats): recA[k] = {W1[k][0..3], b1, b2, w3, br1}, recB[k] = Wr1[k][0..3], recC[k] = Wr2[0..15][k]
+    static constexpr int O_RA = 0;
+    static constexpr int O_RB = O_RA + HID * 8;
+    static constexpr int O_RC = O_RB + HID * 4;
+    static constexpr int SMALL = O_RC + HID * NN;
+    static constexpr int XW = NN + 1 + NS;    // floats per thread in the pair exchange
+    // shared memory map (bytes)
+    static constexpr int OFF_A = 1024;                        // 2 slots x (hi, lo)
+    static constexpr int OFF_B = OFF_A + 4 * A_TILE;          // NBE entries
+    static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE;
+    static constexpr int OFF_XCH = OFF_SMALL + SMALL * 4;
+    static constexpr int SMEM_BYTES = OFF_XCH + XW * 256 * 4;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    // barrier indices
+    static constexpr int B_AFULL = 0, B_AEMPTY = 2, B_BFULL = 4, B_BEMPTY = 4 + NBE, B_ACC = 4 + 2 * NBE, B_SMALL = B_ACC + 2;
+    static constexpr int THREADS = 320;
+};
+
+// big-blob layout for the tensor path: [P: 0 = W2 (B[n=j][k]), 1 = W2^T (B[n=k][K=j])][kb][hi|lo][B_TILE]
+__host__ __device__ inline int sw128_off(int r, int c) {
+    return (r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 2) ^ (r & 7)) & 7) << 4) + (c & 3) * 4;
+}
+
+// ---- tcgen05 helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    // K-major, SWIZZLE_128B, 8-row groups 1024 B apart, descriptor version 1 (validated by tools/tc_probe.cu)
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float dot4(const float4& w, const float (&x)[4], float b) {
+    return fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], b))));
+}
+
+template <class SH> struct TcCtx;
+template <class SH>
+__device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
+template <class SH>
+__device__ __noinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, const float (&v)[4],
+                            float (&xbar)[4], float& ubar);
+
+template <class SH>
+struct TcCtx {
+    static constexpr int NS = SH::NS;
+    static constexpr int TW = SH::TM;
+    static constexpr int WS_EXTRA = SH::HID;
+    int row, hf, lane, barid;
+    uint32_t tlane;  // TMEM base address with this warp's lane quadrant
+    uint32_t ablk;   // A K-blocks produced so far
+    uint32_t qdone;  // products whose accumulator this thread has waited for
+    int split;       // 3 = 3xTF32, 1 = plain TF32
+    float* stash;    // a2 stash of this tile in the workspace: [NKB][128][32]
+    bool store;
+
+    __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(phnn_smem); }
+    __device__ __forceinline__ const float* small() const { return reinterpret_cast<const float*>(phnn_smem + SH::OFF_SMALL); }
+    __device__ __forceinline__ float* xch() const { return reinterpret_cast<float*>(phnn_smem + SH::OFF_XCH); }
+    __device__ __forceinline__ void gbar() const { group_bar(barid, 64); }
+
+    // ---- A-operand ring (element threads are the producers) ----
+    __device__ __forceinline__ int a_begin() const {
+        const int slot = ablk & 1;
+        mbar_wait(&bars()[SH::B_AEMPTY + slot], ((ablk >> 1) & 1u) ^ 1u);
+        return slot;
+    }
+    // four consecutive hidden units (chunk q of this thread's 16) of the current K-block
+    __device__ __forceinline__ void a_put4(int slot, int q, const float (&v)[4]) const {
+        const int ch = hf * 4 + q;
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
+        unsigned char* hi = phnn_smem + SH::OFF_A + (slot * 2) * SH::A_TILE + off;
+        float4 h = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
+        *reinterpret_cast<float4*>(hi) = h;
+        if (split == 3)
+            *reinterpret_cast<float4*>(hi + SH::A_TILE) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+    }
+    __device__ __forceinline__ void a_end(int slot) {
+        tc_fence_before();                                            // earlier tcgen05.ld of this thread are ordered first
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars()[SH::B_AFULL + slot]);
+        ++ablk;
+    }
+    // wait for the next product's accumulator; returns its TMEM address for this thread's lane quadrant
+    __device__ __forceinline__ uint32_t acc_wait() {
+        const uint32_t q = qdone++;
+        mbar_wait(&bars()[SH::B_ACC + (q & 1u)], (q >> 1) & 1u);
+        tc_fence_after();
+        return tlane + (q & 1u) * SH::HID + hf * 16;
+    }
+    // pair exchange: returns mine + partner's for n values starting at slot s0
+    template <int N>
+    __device__ __forceinline__ void exchange(float (&v)[N]) {
+        float* x = xch();
+        const int t = hf * 128 + row;
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i * 256 + t] = v[i];
+        gbar();
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] += x[i * 256 + (t ^ 128)];
+        gbar();
+    }
+    __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[4], float u, float (&f)[4], float& H) {
+        tc_eval_fwd(*this, p, y, u, f, H);
+    }
+    __device__ __forceinline__ void eval_vjp(const KParams& p, const float (&y)[4], float u, const float (&v)[4],
+                                             float (&xbar)[4], float& ubar) {
+        tc_eval_vjp(*this, p, y, u, v, xbar, ubar);
+    }
+};
+
+// S = sym(Rraw + br2)
+__device__ __forceinline__ void tc_make_S(const KParams& p, const float (&Rp)[16], float (&S)[4][4]) {
+    float R[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) R[e] = Rp[e] + p.br2[e];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) S[a][b] = (R[a * 4 + b] + R[b * 4 + a]) * 0.5f;
+}
+
+// ---------------------------------------------------------------------------------------
+// f(y,u), H(y) for the tile's 128 instances (src/pHNN.py:52-100)
+// ---------------------------------------------------------------------------------------
+template <class SH>
+__device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4],
+                                         float& Hval) {
+    constexpr int NKB = SH::NKB;
+    const float* rA = c.small() + SH::O_RA;
+    const float* rB = c.small() + SH::O_RB;
+    const float* rC = c.small() + SH::O_RC;
+    float X[SH::XW];  // [0,16) Rraw partial, [16] H partial, [17,21) dH partial
+#pragma unroll
+    for (int i = 0; i < SH::XW; ++i) X[i] = 0.f;
+    // ---- phase A: a1 -> product 1 (z2 = W2 a1); R_net on the same hidden units ----
+#pragma unroll 1
+    for (int kb = 0; kb < NKB; ++kb) {
+        const int slot = c.a_begin();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float av[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = kb * 32 + c.hf * 16 + q * 4 + e;
+                const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
+                av[e] = tanh_acc(dot4(w1, y, m.x));
+                const float r = tanh_acc(dot4(lds4(rB + k * 4), y, m.w));
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 wc = lds4(rC + k * 16 + c4 * 4);
+                    X[c4 * 4 + 0] = fmaf(wc.x, r, X[c4 * 4 + 0]);
+                    X[c4 * 4 + 1] = fmaf(wc.y, r, X[c4 * 4 + 1]);
+                    X[c4 * 4 + 2] = fmaf(wc.z, r, X[c4 * 4 + 2]);
+                    X[c4 * 4 + 3] = fmaf(wc.w, r, X[c4 * 4 + 3]);
+                }
+            }
+            c.a_put4(slot, q, av);
+        }
+        c.a_end(slot);
+    }
+    // ---- phase B: a2, H, delta2 -> product 2 (g1 = W2^T delta2) ----
+    {
+        const uint32_t tacc = c.acc_wait();
+#pragma unroll 1
+        for (int jb = 0; jb < NKB; ++jb) {
+            float z[16];
+            tmem_ld16(tacc + jb * 32, z);
+            const int slot = c.a_begin();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float dv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = jb * 32 + c.hf * 16 + q * 4 + e;
+                    const float4 m = lds4(rA + j * 8 + 4);
+                    const float a2 = tanh_acc(z[q * 4 + e] + m.y);
+                    X[16] = fmaf(m.z, a2, X[16]);
+                    dv[e] = fmaf(-a2, a2, 1.f) * m.z;
+                }
+                c.a_put4(slot, q, dv);
+            }
+            c.a_end(slot);
+        }
+    }
+    // ---- phase C: dH = W1^T (s1 * g1) ----
+    {
+        const uint32_t tacc = c.acc_wait();
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) {
+            float g1[16];
+            tmem_ld16(tacc + kb * 32, g1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = kb * 32 + c.hf * 16 + i;
+                const float4 w1 = lds4(rA + k * 8);
+                const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
+                const float d1 = fmaf(-a1, a1, 1.f) * g1[i];
+                X[17] = fmaf(w1.x, d1, X[17]);
+                X[18] = fmaf(w1.y, d1, X[18]);
+                X[19] = fmaf(w1.z, d1, X[19]);
+                X[20] = fmaf(w1.w, d1, X[20]);
+            }
+        }
+        tc_fence_before();
+    }
+    c.exchange(X);
+    Hval = X[16] + p.b3;
+    float S[4][4];
+    {
+        float Rp[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) Rp[e] = X[e];
+        tc_make_S(p, Rp, S);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        float s = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float Rab = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) Rab = fmaf(S[a][k], S[b][k], Rab);
+            s = fmaf(p.Jm[a * 4 + b] - Rab, X[17 + b], s);
+        }
+        f[a] = s + p.Gv[a] * u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// xbar = (df/dy)^T v, ubar = (df/du)^T v with recomputed activations and the Hessian-vector
+// product of H_net.  Product order: z2 -> acc0, g1 -> acc1, dz2 -> acc0, dg1 -> acc1.
+// ---------------------------------------------------------------------------------------
+template <class SH>
+__device__ __noinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u,
+                                         const float (&v)[4], float (&xbar)[4], float& ubar) {
+    constexpr int NKB = SH::NKB;
+    const float* rA = c.small() + SH::O_RA;
+    const float* rB = c.small() + SH::O_RB;
+    const float* rC = c.small() + SH::O_RC;
+    float Rp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Rp[i] = 0.f;
+    // ---- A1: a1 -> product 1 ; R_net forward partials ----
+#pragma unroll 1
+    for (int kb = 0; kb < NKB; ++kb) {
+        const int slot = c.a_begin();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float av[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = kb * 32 + c.hf * 16 + q * 4 + e;
+                const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
+                av[e] = tanh_acc(dot4(w1, y, m.x));
+                const float r = tanh_acc(dot4(lds4(rB + k * 4), y, m.w));
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 wc = lds4(rC + k * 16 + c4 * 4);
+                    Rp[c4 * 4 + 0] = fmaf(wc.x, r, Rp[c4 * 4 + 0]);
+                    Rp[c4 * 4 + 1] = fmaf(wc.y, r, Rp[c4 * 4 + 1]);
+                    Rp[c4 * 4 + 2] = fmaf(wc.z, r, Rp[c4 * 4 + 2]);
+                    Rp[c4 * 4 + 3] = fmaf(wc.w, r, Rp[c4 * 4 + 3]);
+                }
+            }
+            c.a_put4(slot, q, av);
+        }
+        c.a_end(slot);
+    }
+    c.exchange(Rp);
+    float S[4][4], sv[4], w[4];
+    tc_make_S(p, Rp, S);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sv[a] = fmaf(S[a][3], v[3], fmaf(S[a][2], v[2], fmaf(S[a][1], v[1], S[a][0] * v[0])));
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {  // w = (J - J^T)^T v - S (S v)
+        float s = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s = fmaf(p.Jm[b * 4 + a], v[b], s);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s = fmaf(-S[a][b], sv[b], s);
+        w[a] = s;
+    }
+    // ---- B1: a2 (stashed), delta2 -> product 2 ----
+    {
+        const uint32_t tacc = c.acc_wait();
+#pragma unroll 1
+        for (int jb = 0; jb < NKB; ++jb) {
+            float z[16];
+            tmem_ld16(tacc + jb * 32, z);
+            const int slot = c.a_begin();
+            float4* st = reinterpret_cast<float4*>(c.stash + ((size_t)(jb * 128 + c.row) * 32 + c.hf * 16));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float dv[4], a2v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = jb * 32 + c.hf * 16 + q * 4 + e;
+                    const float4 m = lds4(rA + j * 8 + 4);
+                    const float a2 = tanh_acc(z[q * 4 + e] + m.y);
+                    a2v[e] = a2;
+                    dv[e] = fmaf(-a2, a2, 1.f) * m.z;
+                }
+                st[q] = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
+                c.a_put4(slot, q, dv);
+            }
+            c.a_end(slot);
+        }
+    }
+    // ---- A3: da1 = s1 * (W1 w) -> product 3 (dz2 = W2 da1) ----
+#pragma unroll 1
+    for (int kb = 0; kb < NKB; ++kb) {
+        const int slot = c.a_begin();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float av[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = kb * 32 + c.hf * 16 + q * 4 + e;
+                const float4 w1 = lds4(rA + k * 8);
+                const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
+                av[e] = fmaf(-a1, a1, 1.f) * dot4(w1, w, 0.f);
+            }
+            c.a_put4(slot, q, av);
+        }
+        c.a_end(slot);
+    }
+    // ---- C2: g1 -> dH partial and the g1 half of xbar_H ----
+    float Y[8];  // [0,4) dH partial, [4,8) xbar partial
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Y[i] = 0.f;
+    {
+        const uint32_t tacc = c.acc_wait();
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) {
+            float g1[16];
+            tmem_ld16(tacc + kb * 32, g1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = kb * 32 + c.hf * 16 + i;
+                const float4 w1 = lds4(rA + k * 8);
+                const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
+                const float s1 = fmaf(-a1, a1, 1.f);
+                const float da1 = s1 * dot4(w1, w, 0.f);
+                const float d1 = s1 * g1[i];
+                const float t = -2.f * a1 * da1 * g1[i];
+                Y[0] = fmaf(w1.x, d1, Y[0]); Y[1] = fmaf(w1.y, d1, Y[1]); Y[2] = fmaf(w1.z, d1, Y[2]); Y[3] = fmaf(w1.w, d1, Y[3]);
+                Y[4] = fmaf(w1.x, t, Y[4]); Y[5] = fmaf(w1.y, t, Y[5]); Y[6] = fmaf(w1.z, t, Y[6]); Y[7] = fmaf(w1.w, t, Y[7]);
+            }
+        }
+    }
+    // ---- B3: e2 = -2 a2 da2 w3 -> product 4 (dg1 = W2^T e2) ----
+    {
+        const uint32_t tacc = c.acc_wait();
+#pragma unroll 1
+        for (int jb = 0; jb < NKB; ++jb) {
+            float dz[16];
+            tmem_ld16(tacc + jb * 32, dz);
+            const int slot = c.a_begin();
+            const float4* st = reinterpret_cast<const float4*>(c.stash + ((size_t)(jb * 128 + c.row) * 32 + c.hf * 16));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 a2q = st[q];
+                const float a2v[4] = {a2q.x, a2q.y, a2q.z, a2q.w};
+                float ev[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = jb * 32 + c.hf * 16 + q * 4 + e;
+                    const float w3 = rA[j * 8 + 6];
+                    const float da2 = fmaf(-a2v[e], a2v[e], 1.f) * dz[q * 4 + e];
+                    ev[e] = -2.f * a2v[e] * da2 * w3;
+                }
+                c.a_put4(slot, q, ev);
+            }
+            c.a_end(slot);
+        }
+    }
+    // ---- while product 4 runs: dH total, then the R_net chain (thread-local over my hidden units) ----
+    float G4[4] = {Y[0], Y[1], Y[2], Y[3]};
+    c.exchange(G4);
+    float X4[4] = {Y[4], Y[5], Y[6], Y[7]};
+    {
+        float tg[4], Rb[16];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tg[a] = fmaf(S[a][3], G4[3], fmaf(S[a][2], G4[2], fmaf(S[a][1], G4[1], S[a][0] * G4[0])));
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) Rb[a * 4 + b] = -0.5f * (v[a] * tg[b] + G4[a] * sv[b] + v[b] * tg[a] + G4[b] * sv[a]);
+#pragma unroll 1
+        for (int kk = 0; kk < SH::HID / 2; ++kk) {
+            const int k = (kk >> 4) * 32 + c.hf * 16 + (kk & 15);
+            float rb = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 wc = lds4(rC + k * 16 + c4 * 4);
+                rb = fmaf(wc.x, Rb[c4 * 4 + 0], rb);
+                rb = fmaf(wc.y, Rb[c4 * 4 + 1], rb);
+                rb = fmaf(wc.z, Rb[c4 * 4 + 2], rb);
+                rb = fmaf(wc.w, Rb[c4 * 4 + 3], rb);
+            }
+            const float4 wr = lds4(rB + k * 4);
+            const float r1 = tanh_acc(dot4(wr, y, rA[k * 8 + 7]));
+            const float zb = rb * fmaf(-r1, r1, 1.f);
+            X4[0] = fmaf(wr.x, zb, X4[0]); X4[1] = fmaf(wr.y, zb, X4[1]); X4[2] = fmaf(wr.z, zb, X4[2]); X4[3] = fmaf(wr.w, zb, X4[3]);
+        }
+    }
+    // ---- C4: the dg1 half of xbar_H ----
+    {
+        const uint32_t tacc = c.acc_wait();
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) {
+            float dg[16];
+            tmem_ld16(tacc + kb * 32, dg);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = kb * 32 + c.hf * 16 + i;
+                const float4 w1 = lds4(rA + k * 8);
+                const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
+                const float t = fmaf(-a1, a1, 1.f) * dg[i];
+                X4[0] = fmaf(w1.x, t, X4[0]); X4[1] = fmaf(w1.y, t, X4[1]); X4[2] = fmaf(w1.z, t, X4[2]); X4[3] = fmaf(w1.w, t, X4[3]);
+            }
+        }
+        tc_fence_before();
+    }
+    c.exchange(X4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xbar[i] = X4[i];
+    ubar = fmaf(p.Gv[3], v[3], fmaf(p.Gv[2], v[2], fmaf(p.Gv[1], v[1], p.Gv[0] * v[0])));
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <int MK, int NS, int HID>
+__global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__ KParams p) {
+    using SH = TcShape<MK, NS, HID>;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 512);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[SH::B_AFULL + 0], 8);
+        mbar_init(&bars[SH::B_AFULL + 1], 8);
+        mbar_init(&bars[SH::B_AEMPTY + 0], 1);
+        mbar_init(&bars[SH::B_AEMPTY + 1], 1);
+        for (int e = 0; e < SH::NBE; ++e) {
+            mbar_init(&bars[SH::B_BFULL + e], 1);
+            mbar_init(&bars[SH::B_BEMPTY + e], 1);
+        }
+        mbar_init(&bars[SH::B_ACC + 0], 1);
+        mbar_init(&bars[SH::B_ACC + 1], 1);
+        mbar_init(&bars[SH::B_SMALL], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"((uint32_t)SH::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_ptr;
+
+    // evaluation schedule (same derivation as phnn_kernel)
+    const int E = p.T * p.S;
+    int n_outer = 1, nfwd = 0, nadj = 0;
+    switch (p.mode) {
+        case MODE_FORWARD: nfwd = 1; break;
+        case MODE_VJP: nadj = 1; break;
+        case MODE_ROLLOUT: nfwd = E + (p.energy_mode == 2 ? 1 : 0); break;
+        case MODE_COSTGRAD: nfwd = E; nadj = p.want_grad ? E : 0; break;
+        default: n_outer = p.iters; nfwd = E; nadj = E; break;
+    }
+    const long long nprod = (long long)n_outer * (2LL * nfwd + 4LL * nadj);
+    const int split = p.tc_split;
+
+    if (warp < 8) {
+        // ===== element threads =====
+        TcCtx<SH> c;
+        c.row = threadIdx.x & 127;
+        c.hf = threadIdx.x >> 7;
+        c.lane = lane;
+        c.barid = 1 + (warp & 3);
+        c.tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+        c.ablk = 0;
+        c.qdone = 0;
+        c.split = split;
+        c.store = (c.hf == 0);
+        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, 128, HID);
+        c.stash = p.ws ? p.ws + (size_t)blockIdx.x * tile_floats + ws_floats_per_tile(NS, p.T, p.S, 128, 0) : nullptr;
+        mbar_wait(&bars[SH::B_SMALL], 0);
+        run_job(c, p, (long long)blockIdx.x, c.row, n_outer);
+        tc_fence_before();
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t a_base = smem_u32(phnn_smem + SH::OFF_A), b_base = smem_u32(phnn_smem + SH::OFF_B);
+            uint32_t ablk = 0, bent = 0;
+#pragma unroll 1
+            for (long long q = 0; q < nprod; ++q) {
+                const uint32_t acc = tbase + (uint32_t)(q & 1) * HID;
+#pragma unroll 1
+                for (int kb = 0; kb < SH::NKB; ++kb) {
+                    const uint32_t slot = ablk & 1u;
+                    mbar_wait(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u);
+                    const uint32_t a_hi = a_base + (slot * 2) * SH::A_TILE, a_lo = a_hi + SH::A_TILE;
+                    uint32_t e = bent % SH::NBE;
+                    mbar_wait(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
+                    tc_fence_after();
+                    uint32_t b_t = b_base + e * SH::B_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, (kb | ks) ? 1u : 0u);
+                    if (split == 3) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_tf32(acc, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
+                    }
+                    umma_commit(&bars[SH::B_BEMPTY + e]);
+                    ++bent;
+                    if (split == 3) {
+                        e = bent % SH::NBE;
+                        mbar_wait(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
+                        tc_fence_after();
+                        b_t = b_base + e * SH::B_TILE;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
+                        umma_commit(&bars[SH::B_BEMPTY + e]);
+                        ++bent;
+                    }
+                    umma_commit(&bars[SH::B_AEMPTY + slot]);
+                    ++ablk;
+                }
+                umma_commit(&bars[SH::B_ACC + (q & 1)]);
+            }
+        }
+    } else {
+        // ===== weight producer (TMA bulk copies of pre-swizzled K-blocks) =====
+        if (lane == 0) {
+            mbar_expect_tx(&bars[SH::B_SMALL], SH::SMALL * 4);
+            bulk_g2s(phnn_smem + SH::OFF_SMALL, p.wsmall_tc, SH::SMALL * 4, &bars[SH::B_SMALL]);
+            uint32_t bent = 0;
+#pragma unroll 1
+            for (long long q = 0; q < nprod; ++q) {
+                const unsigned char* src = p.wtc + (size_t)(q & 1) * SH::NKB * 2 * SH::B_TILE;
+#pragma unroll 1
+                for (int kb = 0; kb < SH::NKB; ++kb) {
+                    for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
+                        const uint32_t e = bent % SH::NBE;
+                        mbar_wait(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u);
+                        mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
+                        bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)(kb * 2 + hl) * SH::B_TILE, SH::B_TILE,
+                                 &bars[SH::B_BFULL + e]);
+                        ++bent;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"((uint32_t)SH::TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace phnn

@@ -98,6 +98,14 @@ class PackedModel:
         self.handle = handle.value
         self._fin = weakref.finalize(self, L.phnn_pack_destroy, ctypes.c_void_p(self.handle))
 
+    def set_option(self, key, value):
+        """kernel selection knobs: 'tensor_mode' (0 FP32-FMA, 3 tcgen05 3xTF32, 1 tcgen05 TF32), 'tensor_min_batch'"""
+        _lib.check(_lib.lib().phnn_pack_set_option(ctypes.c_void_p(self.handle), key.encode(), int(value)),
+                   "phnn_pack_set_option")
+
+    def get_option(self, key):
+        return int(_lib.lib().phnn_pack_get_option(ctypes.c_void_p(self.handle), key.encode()))
+
     def __int__(self):
         return self.handle
 

@@ -9,11 +9,15 @@ from phnn_mpc_b200.packing import PackedModel
 
 KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical"}
 cu = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
-names = sys.argv[1:] or list(KINDS)
+TC = os.environ.get("PHNN_TC")
+names = [a for a in sys.argv[1:]] or list(KINDS)
 for name in names:
     z, sd = load_golden(name)
     pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, KINDS[name])
-    print(name, "packed", flush=True)
+    if TC is not None:
+        pk.set_option("tensor_min_batch", 0)
+        pk.set_option("tensor_mode", int(TC))
+    print(name, "packed; tensor_mode", pk.get_option("tensor_mode"), flush=True)
     dx, H = ops.forward(pk.handle, cu(z["rand_x"]), cu(z["rand_u"])); torch.cuda.synchronize()
     print("  fwd  dx %.2e  H %.2e" % (rel_err(dx.cpu().numpy(), z["rand_dx"]), rel_err(H.cpu().numpy(), z["rand_H"])), flush=True)
     xb, ub = ops.vjp(pk.handle, cu(z["rand_x"]), cu(z["rand_u"]), cu(z["rand_v"])); torch.cuda.synchronize()
@@ -23,6 +27,8 @@ for name in names:
     dt, lr = float(z["mpc_dt"]), float(z["mpc_lr"])
     for integ, iid in (("euler", 0), ("rk4", 1)):
         p = "mpc_%s_" % integ
+        tr2, _ = ops.rollout(pk.handle, cu(z["mpc_x0"]), cu(np.clip(z["mpc_U0"], lo, hi)), dt, iid, 0); torch.cuda.synchronize()
+        if p + "traj0" in z.files: print("  %s rollout %.2e" % (integ, rel_err(tr2.cpu().numpy(), z[p + "traj0"])), flush=True)
         cost, g, tr = ops.cost_grad(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, True, True); torch.cuda.synchronize()
         print("  %s cost %.2e grad %.2e" % (integ, rel_err(cost.cpu().numpy(), z[p + "hist"][0]), rel_err(g.cpu().numpy(), z[p + "grad0"])), flush=True)
         iters = z[p + "hist"].shape[0]
