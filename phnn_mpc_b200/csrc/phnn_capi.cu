@@ -101,9 +101,11 @@ static void fill_tc_big(const phnn_model_desc* d, std::vector<unsigned char>& ou
                 }
 }
 
+// recA[k] = {W1[k][0..3], b1, b2, w3, br1}, recB[k] = Wr1[k][0..3], recC[k] = 10 symmetrised R_net
+// output weights + 2 pad
 static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
-    const int h = d->h, n = d->n, nn = n * n;
-    s.assign((size_t)h * (8 + 4 + nn), 0.f);
+    const int h = d->h, n = d->n;   // n == 4 for every tcgen05 shape
+    s.assign((size_t)h * (8 + 4 + 12), 0.f);
     float* rA = s.data();
     float* rB = rA + (size_t)h * 8;
     float* rC = rB + (size_t)h * 4;
@@ -114,7 +116,9 @@ static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
         rA[k * 8 + 6] = d->W3[k];
         rA[k * 8 + 7] = d->br1[k];
         for (int i = 0; i < n; ++i) rB[k * 4 + i] = d->Wr1[k * n + i];
-        for (int c = 0; c < nn; ++c) rC[k * nn + c] = d->Wr2[(size_t)c * h + k];
+        for (int a = 0; a < n; ++a)
+            for (int b = a; b < n; ++b)
+                rC[k * 12 + sym_idx(a, b)] = 0.5f * (d->Wr2[(size_t)(a * n + b) * h + k] + d->Wr2[(size_t)(b * n + a) * h + k]);
     }
 }
 
@@ -226,8 +230,12 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
             P.Jm[a * n + b] = (mk == MK_CANON) ? d->J[a * n + b] : (d->J[a * n + b] - d->J[b * n + a]);
     for (int a = 0; a < n; ++a) P.Gv[a] = d->G ? d->G[a] : 0.f;
     P.b3 = d->b3[0];
-    if (mk != MK_CANON)
+    if (mk != MK_CANON) {
         for (int e2 = 0; e2 < n * n; ++e2) P.br2[e2] = d->br2[e2];
+        if (n == 4)
+            for (int a = 0; a < 4; ++a)
+                for (int b = a; b < 4; ++b) P.bsym[sym_idx(a, b)] = 0.5f * (d->br2[a * 4 + b] + d->br2[b * 4 + a]);
+    }
     if (mk == MK_PHNN_GNET)
         for (int a = 0; a < n; ++a) P.bg2[a] = d->bg2[a];
     if (mk == MK_CANON) {
@@ -262,6 +270,10 @@ extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) 
     }
     return fail(PHNN_E_ARG, "unknown option %s", key);
 }
+
+// debug: device buffer (32 x int64) that PHNN_TC_PROFILE builds fill with per-phase cycle counts
+static long long* g_dbg = nullptr;
+extern "C" void phnn_debug_set_buffer(void* p) { g_dbg = (long long*)p; }
 
 extern "C" long phnn_pack_get_option(const phnn_pack* pk, const char* key) {
     if (!pk || !key) return -1;
@@ -303,6 +315,7 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
     P.tc_split = pk->tc_mode == 1 ? 1 : 3;
     P.ng = 1;
+    P.dbg = g_dbg;
     kern<<<(unsigned)tiles, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -407,7 +420,7 @@ extern "C" size_t phnn_workspace_bytes(const phnn_pack* pk, long B, int T, int i
     if (!pk || B <= 0 || T <= 0) return 0;
     // sized for 128-instance tiles (the tcgen05 kernel); a superset of what 32-instance tiles need
     const size_t tiles = ((size_t)B + 127) / 128;
-    return tiles * ws_floats_per_tile(pk->n, T, integrator == PHNN_RK4 ? 4 : 1, 128, pk->h) * sizeof(float);
+    return tiles * ws_floats_per_tile(pk->n, T, integrator == PHNN_RK4 ? 4 : 1, 128, 2 * pk->h) * sizeof(float);
 }
 
 extern "C" int phnn_cost_grad(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, const float* U,

@@ -88,6 +88,7 @@ struct KParams {
     float Gv[4];
     float b3, ma, mb, mc;
     float br2[16];
+    float bsym[12];  // tcgen05 path: (br2[ab] + br2[ba])/2 packed 00 01 02 03 11 12 13 22 23 33
     float bg2[4];
     float rdiag[4];
     // cost
@@ -112,6 +113,7 @@ struct KParams {
     float* dJdU;       // COSTGRAD [B,T] (nullable)
     float* cost_hist;  // SOLVE [iters,B] (nullable)
     float* ws;         // workspace
+    long long* dbg;    // optional profiling output (PHNN_TC_PROFILE builds)
 };
 
 // floats of workspace per tile of TW instances: stage states [T*S][NS][TW], Adam m, v and best
@@ -935,48 +937,26 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
     const long long b = tile * TW + slot;  // my instance
     const bool valid = b < p.B;
     const bool st = valid && c.store;
-    const int T = p.T, S = p.S;
+    const int T = p.T, S = p.S;  // MODE_FORWARD / MODE_VJP arrive with T = S = 1
     const int E = T * S;
 
     float x0[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) x0[i] = valid ? p.x0[b * NS + i] : 0.f;
 
-    if (p.mode == MODE_FORWARD) {
-        const float u = valid ? p.uin[b] : 0.f;
-        float f[NS], Hv;
-        c.eval_fwd(p, x0, u, f, Hv);
-        if (st) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = f[i];
-            p.out1[b] = Hv;
-        }
-        return;
-    }
-    if (p.mode == MODE_VJP) {
-        const float u = valid ? p.uin[b] : 0.f;
-        float v[NS], xb[NS], ub;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) v[i] = valid ? p.vin[b * NS + i] : 0.f;
-        c.eval_vjp(p, x0, u, v, xb, ub);
-        if (st) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = xb[i];
-            p.out1[b] = ub;
-        }
-        return;
-    }
-
-    // workspace of this group: stage states [E][NS][32], Adam m/v and best controls [T][32]
+    // workspace of this tile: stage states [E][NS][TW], Adam m/v and best controls [T][TW]
     float* wsg = p.ws ? p.ws + (size_t)tile * ws_floats_per_tile(NS, T, S, TW, ENG::WS_EXTRA) : nullptr;
     float* ckpt = wsg;
     float* adam_m = wsg ? wsg + (size_t)E * NS * TW : nullptr;
     float* adam_v = adam_m ? adam_m + (size_t)T * TW : nullptr;
     float* ubest = adam_v ? adam_v + (size_t)T * TW : nullptr;
     const bool solve = (p.mode == MODE_SOLVE);
-    const bool need_adj = solve || (p.mode == MODE_COSTGRAD && p.want_grad);
+    const bool one_vjp = (p.mode == MODE_VJP);
+    const bool need_adj = solve || one_vjp || (p.mode == MODE_COSTGRAD && p.want_grad);
     const float* Uread = solve ? p.U : p.uin;
-    float* traj = (p.mode == MODE_SOLVE) ? nullptr : p.out0;
+    float* traj = (p.mode == MODE_ROLLOUT || p.mode == MODE_COSTGRAD) ? p.out0 : nullptr;
+    // rollout_trajectory's energy list needs one more evaluation, at y_T (src/integrators.py:184)
+    const int t_end = one_vjp ? 0 : T + ((p.mode == MODE_ROLLOUT && p.energy_mode == 2) ? 1 : 0);
 
     if (solve && st) {
         for (int t = 0; t < T; ++t) {
@@ -995,10 +975,11 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
         for (int i = 0; i < NS; ++i) x[i] = x0[i];
         float cost = 0.f;
 #pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-            const float uraw = valid ? __ldcg(Uread + b * T + t) : 0.f;
+        for (int t = 0; t < t_end; ++t) {
+            const bool tail = (t == T);  // energy-only evaluation at the final state
+            const float uraw = (valid && !tail) ? __ldcg(Uread + b * T + t) : 0.f;
             const float u = clampu(p, uraw);
-            if (p.mode != MODE_ROLLOUT) {
+            if (p.mode == MODE_COSTGRAD || solve) {
                 cost += state_cost<NS>(p, x, nullptr);
                 cost = fmaf(p.Rw * u, u, cost);
             }
@@ -1016,6 +997,14 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
                     for (int i = 0; i < NS; ++i) ckpt[((size_t)(t * S + s) * NS + i) * TW + slot] = ys[i];
                 }
                 c.eval_fwd(p, ys, u, k, Hv);
+                if (p.mode == MODE_FORWARD) {
+                    if (st) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = k[i];
+                        p.out1[b] = Hv;
+                    }
+                    return;
+                }
                 if (s == 0 && p.mode == MODE_ROLLOUT && p.out1 && st) {
                     // H(y_t): differentiable-rollout ordering puts it at index t+1 (and 0)
                     if (p.energy_mode == 1) {
@@ -1025,6 +1014,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
                         p.out1[b * (T + 1) + t] = Hv;
                     }
                 }
+                if (tail) break;
                 if (S == 1) {
 #pragma unroll
                     for (int i = 0; i < NS; ++i) x[i] = fmaf(p.dt, k[i], x[i]);
@@ -1046,19 +1036,12 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
                 }
             }
         }
-        if (p.mode != MODE_ROLLOUT) cost += state_cost<NS>(p, x, nullptr);
-        if (traj && st) {
+        if (p.mode == MODE_COSTGRAD || solve) cost += state_cost<NS>(p, x, nullptr);
+        if (traj && st && t_end == T) {
 #pragma unroll
             for (int i = 0; i < NS; ++i) traj[(b * (T + 1) + T) * NS + i] = x[i];
         }
-        if (p.mode == MODE_ROLLOUT) {
-            if (p.energy_mode == 2) {
-                float k[NS], Hv;
-                c.eval_fwd(p, x, 0.f, k, Hv);
-                if (p.out1 && st) p.out1[b * (T + 1) + T] = Hv;
-            }
-            return;
-        }
+        if (p.mode == MODE_ROLLOUT) return;
         if (p.mode == MODE_COSTGRAD && st) p.cost[b] = cost;
         if (solve && st && p.cost_hist) p.cost_hist[(size_t)(it - 1) * p.B + b] = cost;
         if (!need_adj) return;
@@ -1077,36 +1060,54 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
         const float w1 = (float)(1.0 - p.beta1), b2f = (float)p.beta2, w2 = (float)(1.0 - p.beta2), epsf = (float)p.eps;
 
         float lam[NS];
-        state_cost<NS>(p, x, lam);
+        if (one_vjp) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) lam[i] = valid ? p.vin[b * NS + i] : 0.f;
+        } else {
+            state_cost<NS>(p, x, lam);
+        }
 #pragma unroll 1
         for (int t = T - 1; t >= 0; --t) {
             const float uraw = valid ? __ldcg(Uread + b * T + t) : 0.f;
-            const float u = clampu(p, uraw);
+            const float u = one_vjp ? uraw : clampu(p, uraw);
             float ubsum = 0.f, y[NS], xb[NS], ub, kb[NS], ysum[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) ysum[i] = 0.f;
+            for (int i = 0; i < NS; ++i) { ysum[i] = 0.f; xb[i] = 0.f; }
 #pragma unroll 1
             for (int s = S - 1; s >= 0; --s) {
+                if (one_vjp) {
 #pragma unroll
-                for (int i = 0; i < NS; ++i)
-                    y[i] = valid ? __ldcg(ckpt + ((size_t)(t * S + s) * NS + i) * TW + slot) : 0.f;
-                if (S == 1) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = p.dt * lam[i];
-                } else if (s == 3) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = p.dt6 * lam[i];
-                } else if (s == 2) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt * xb[i]);
-                } else if (s == 1) {
-#pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt2 * xb[i]);
+                    for (int i = 0; i < NS; ++i) { y[i] = x0[i]; kb[i] = lam[i]; }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt6, lam[i], p.dt2 * xb[i]);
+                    for (int i = 0; i < NS; ++i)
+                        y[i] = valid ? __ldcg(ckpt + ((size_t)(t * S + s) * NS + i) * TW + slot) : 0.f;
+                    if (S == 1) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) kb[i] = p.dt * lam[i];
+                    } else if (s == 3) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) kb[i] = p.dt6 * lam[i];
+                    } else if (s == 2) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt * xb[i]);
+                    } else if (s == 1) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt3, lam[i], p.dt2 * xb[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt6, lam[i], p.dt2 * xb[i]);
+                    }
                 }
                 c.eval_vjp(p, y, u, kb, xb, ub);
+                if (one_vjp) {
+                    if (st) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = xb[i];
+                        p.out1[b] = ub;
+                    }
+                    return;
+                }
                 ubsum += ub;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) ysum[i] += xb[i];
@@ -1131,8 +1132,8 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
                 p.U[b * T + t] = uraw + (-step_size * m) / den;
             }
         }
-        // the storing warp's update of U[.,0] must be visible to the group's other warps before
-        // they re-read it at the top of the next forward sweep
+        // the storing thread's update of U[.,0] must be visible to the instance's other owners
+        // before they re-read it at the top of the next forward sweep
         c.gbar();
     }
     if (solve && st) {

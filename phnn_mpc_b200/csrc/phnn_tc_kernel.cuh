@@ -38,12 +38,14 @@ struct TcShape {
     static constexpr int B_TILE = HID * 128;  // bytes of one B K-block (hi or lo)
     static constexpr int NBE = 3;             // B ring entries
     static constexpr int TMEM_COLS = (2 * HID <= 32) ? 32 : (2 * HID <= 64) ? 64 : (2 * HID <= 128) ? 128 : (2 * HID <= 256) ? 256 : 512;
-    // small weights (floats): recA[k] = {W1[k][0..3], b1, b2, w3, br1}, recB[k] = Wr1[k][0..3], recC[k] = Wr2[0..15][k]
+    // small weights (floats): recA[k] = {W1[k][0..3], b1, b2, w3, br1}, recB[k] = Wr1[k][0..3],
+    // recC[k] = the 10 symmetrised R_net output weights (Wr2[ab][k] + Wr2[ba][k])/2, a <= b, + 2 pad
+    static constexpr int NSYM = 10, RC = 12;
     static constexpr int O_RA = 0;
     static constexpr int O_RB = O_RA + HID * 8;
     static constexpr int O_RC = O_RB + HID * 4;
-    static constexpr int SMALL = O_RC + HID * NN;
-    static constexpr int XW = NN + 1 + NS;    // floats per thread in the pair exchange
+    static constexpr int SMALL = O_RC + HID * RC;
+    static constexpr int XW = 12 + 1 + NS;    // floats per thread in the pair exchange (S partial, H, dH)
     // shared memory map (bytes)
     static constexpr int OFF_A = 1024;                        // 2 slots x (hi, lo)
     static constexpr int OFF_B = OFF_A + 4 * A_TILE;          // NBE entries
@@ -78,46 +80,86 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// round-to-nearest TF32 of a finite float in two integer ops (cvt.rna.tf32.f32 expands to four on
+// sm_100a because of its Inf/NaN guard; activations here are finite)
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// keeps the compiler from hoisting the next chunk's loads above this point: without it ptxas
+// front-loads a whole K-block of weight loads and then serialises the tanh chains on one register
+__device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
+// asynchronous TMEM load of 16 consecutive columns of this thread's lane; the registers are
+// valid only after tmem_wait16 (which also ties them to the wait for the compiler)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// visit the NKB 32-column blocks of an accumulator with the next block's load in flight while
+// the current one is processed: body(block index, 16 values of this thread's half)
+template <int NKB, class F>
+__device__ __forceinline__ void for_acc_blocks(uint32_t tacc, F&& body) {
+    uint32_t ra[16], rb[16];
+    tmem_ld16_issue(tacc, ra);
+#pragma unroll 1
+    for (int b = 0; b < NKB; b += 2) {
+        tmem_wait16(ra);
+        tmem_ld16_issue(tacc + (b + 1) * 32, rb);
+        body(b, ra);
+        tmem_wait16(rb);
+        if (b + 2 < NKB) tmem_ld16_issue(tacc + (b + 2) * 32, ra);
+        body(b + 1, rb);
+    }
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try(bar, parity)) __nanosleep(ns);
 }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float dot4(const float4& w, const float (&x)[4], float b) {
     return fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], b))));
 }
 
+#ifdef PHNN_TC_PROFILE
+#define TCP_MARK(c, i) do { long long t_ = clock64(); (c).prof[i] += t_ - (c).tlast; (c).tlast = t_; } while (0)
+#else
+#define TCP_MARK(c, i) do { } while (0)
+#endif
+
 template <class SH> struct TcCtx;
 template <class SH>
-__device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
+__device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
 template <class SH>
-__device__ __noinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, const float (&v)[4],
+__device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, const float (&v)[4],
                             float (&xbar)[4], float& ubar);
 
 template <class SH>
 struct TcCtx {
     static constexpr int NS = SH::NS;
     static constexpr int TW = SH::TM;
-    static constexpr int WS_EXTRA = SH::HID;
+    static constexpr int WS_EXTRA = 2 * SH::HID;  // a1 and a2 stashes
     int row, hf, lane, barid;
     uint32_t tlane;  // TMEM base address with this warp's lane quadrant
     uint32_t ablk;   // A K-blocks produced so far
     uint32_t qdone;  // products whose accumulator this thread has waited for
     int split;       // 3 = 3xTF32, 1 = plain TF32
-    float* stash;    // a2 stash of this tile in the workspace: [NKB][128][32]
+    float* stash;    // activation stashes of this tile in the workspace (a2 then a1), each [NKB][2][4][128] float4,
+                     // so a warp's 32 rows read/write 512 contiguous bytes
     bool store;
+#ifdef PHNN_TC_PROFILE
+    long long prof[16];
+    long long tlast;
+    long long await[8];  // a_begin wait cycles per producing phase
+    int aphase;
+#endif
 
     __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(phnn_smem); }
     __device__ __forceinline__ const float* small() const { return reinterpret_cast<const float*>(phnn_smem + SH::OFF_SMALL); }
@@ -125,9 +167,16 @@ struct TcCtx {
     __device__ __forceinline__ void gbar() const { group_bar(barid, 64); }
 
     // ---- A-operand ring (element threads are the producers) ----
-    __device__ __forceinline__ int a_begin() const {
+    __device__ __forceinline__ int a_begin() {
         const int slot = ablk & 1;
+#ifdef PHNN_TC_PROFILE
+        const long long t0 = clock64();
+#endif
         mbar_wait(&bars()[SH::B_AEMPTY + slot], ((ablk >> 1) & 1u) ^ 1u);
+#ifdef PHNN_TC_PROFILE
+        const long long t1 = clock64();
+        await[aphase] += t1 - t0;
+#endif
         return slot;
     }
     // four consecutive hidden units (chunk q of this thread's 16) of the current K-block
@@ -154,6 +203,14 @@ struct TcCtx {
         tc_fence_after();
         return tlane + (q & 1u) * SH::HID + hf * 16;
     }
+    // float4 slot of (stash which, K-block jb, chunk q) for this thread
+    __device__ __forceinline__ float4* stash4(int which, int jb, int q) const {
+        return reinterpret_cast<float4*>(stash) + ((size_t)which * SH::NKB * 8 + (jb * 2 + hf) * 4 + q) * 128 + row;
+    }
+    __device__ __forceinline__ void stash_load(int which, int jb, float4 (&v)[4]) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = __ldcg(stash4(which, jb, q));
+    }
     // pair exchange: returns mine + partner's for n values starting at slot s0
     template <int N>
     __device__ __forceinline__ void exchange(float (&v)[N]) {
@@ -175,33 +232,36 @@ struct TcCtx {
     }
 };
 
-// S = sym(Rraw + br2)
-__device__ __forceinline__ void tc_make_S(const KParams& p, const float (&Rp)[16], float (&S)[4][4]) {
-    float R[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) R[e] = Rp[e] + p.br2[e];
+// index of the symmetric pair (a,b) in the 10-entry packed order 00 01 02 03 11 12 13 22 23 33
+__host__ __device__ constexpr int sym_idx(int a, int b) {
+    return a <= b ? (a * 4 - a * (a - 1) / 2 + (b - a)) : (b * 4 - b * (b - 1) / 2 + (a - b));
+}
+// S = (Rraw + Rraw^T)/2 from the packed symmetric sums (weights and biases were symmetrised on
+// the host: S is linear in the R_net output, src/pHNN.py:79)
+__device__ __forceinline__ void tc_make_S(const KParams& p, const float* Sp, float (&S)[4][4]) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) S[a][b] = (R[a * 4 + b] + R[b * 4 + a]) * 0.5f;
+        for (int b = 0; b < 4; ++b) S[a][b] = Sp[sym_idx(a, b)] + p.bsym[sym_idx(a, b)];
+}
+// accumulate r * recC[k] into the 10 packed S sums
+__device__ __forceinline__ void tc_acc_S(const float* rC, int k, float r, float* Sp) {
+    const float4 c0 = lds4(rC + k * 12), c1 = lds4(rC + k * 12 + 4);
+    const float2 c2 = *reinterpret_cast<const float2*>(rC + k * 12 + 8);
+    Sp[0] = fmaf(c0.x, r, Sp[0]); Sp[1] = fmaf(c0.y, r, Sp[1]); Sp[2] = fmaf(c0.z, r, Sp[2]); Sp[3] = fmaf(c0.w, r, Sp[3]);
+    Sp[4] = fmaf(c1.x, r, Sp[4]); Sp[5] = fmaf(c1.y, r, Sp[5]); Sp[6] = fmaf(c1.z, r, Sp[6]); Sp[7] = fmaf(c1.w, r, Sp[7]);
+    Sp[8] = fmaf(c2.x, r, Sp[8]); Sp[9] = fmaf(c2.y, r, Sp[9]);
 }
 
-// ---------------------------------------------------------------------------------------
-// f(y,u), H(y) for the tile's 128 instances (src/pHNN.py:52-100)
-// ---------------------------------------------------------------------------------------
-template <class SH>
-__device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4],
-                                         float& Hval) {
-    constexpr int NKB = SH::NKB;
+// phase A of both evaluations: a1 = tanh(W1 y + b1) -> A ring (product z2 = W2 a1), and the
+// R_net hidden layer with its symmetrised output sums
+template <bool STASH, class SH>
+__device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&y)[4], float* Sp) {
     const float* rA = c.small() + SH::O_RA;
     const float* rB = c.small() + SH::O_RB;
     const float* rC = c.small() + SH::O_RC;
-    float X[SH::XW];  // [0,16) Rraw partial, [16] H partial, [17,21) dH partial
-#pragma unroll
-    for (int i = 0; i < SH::XW; ++i) X[i] = 0.f;
-    // ---- phase A: a1 -> product 1 (z2 = W2 a1); R_net on the same hidden units ----
 #pragma unroll 1
-    for (int kb = 0; kb < NKB; ++kb) {
+    for (int kb = 0; kb < SH::NKB; ++kb) {
         const int slot = c.a_begin();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -212,26 +272,42 @@ __device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const f
                 const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
                 av[e] = tanh_acc(dot4(w1, y, m.x));
                 const float r = tanh_acc(dot4(lds4(rB + k * 4), y, m.w));
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 wc = lds4(rC + k * 16 + c4 * 4);
-                    X[c4 * 4 + 0] = fmaf(wc.x, r, X[c4 * 4 + 0]);
-                    X[c4 * 4 + 1] = fmaf(wc.y, r, X[c4 * 4 + 1]);
-                    X[c4 * 4 + 2] = fmaf(wc.z, r, X[c4 * 4 + 2]);
-                    X[c4 * 4 + 3] = fmaf(wc.w, r, X[c4 * 4 + 3]);
-                }
+                tc_acc_S(rC, k, r, Sp);
             }
+            if (STASH) *c.stash4(1, kb, q) = make_float4(av[0], av[1], av[2], av[3]);
             c.a_put4(slot, q, av);
+            sched_fence();
         }
         c.a_end(slot);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// f(y,u), H(y) for the tile's 128 instances (src/pHNN.py:52-100)
+// ---------------------------------------------------------------------------------------
+template <class SH>
+__device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4],
+                                         float& Hval) {
+    constexpr int NKB = SH::NKB;
+    const float* rA = c.small() + SH::O_RA;
+    float X[SH::XW];  // [0,10) S sums, [12] H partial, [13,17) dH partial
+#pragma unroll
+    for (int i = 0; i < SH::XW; ++i) X[i] = 0.f;
+    TCP_MARK(c, 15);
+#ifdef PHNN_TC_PROFILE
+    c.aphase = 0;
+#endif
+    tc_phase_a1<false>(c, y, X);
+#ifdef PHNN_TC_PROFILE
+    c.aphase = 1;
+#endif
+    TCP_MARK(c, 0);
     // ---- phase B: a2, H, delta2 -> product 2 (g1 = W2^T delta2) ----
     {
         const uint32_t tacc = c.acc_wait();
-#pragma unroll 1
-        for (int jb = 0; jb < NKB; ++jb) {
-            float z[16];
-            tmem_ld16(tacc + jb * 32, z);
+        TCP_MARK(c, 1);
+        float Hp = 0.f;
+        for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&zr)[16]) {
             const int slot = c.a_begin();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -240,45 +316,43 @@ __device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const f
                 for (int e = 0; e < 4; ++e) {
                     const int j = jb * 32 + c.hf * 16 + q * 4 + e;
                     const float4 m = lds4(rA + j * 8 + 4);
-                    const float a2 = tanh_acc(z[q * 4 + e] + m.y);
-                    X[16] = fmaf(m.z, a2, X[16]);
+                    const float a2 = tanh_acc(__uint_as_float(zr[q * 4 + e]) + m.y);
+                    Hp = fmaf(m.z, a2, Hp);
                     dv[e] = fmaf(-a2, a2, 1.f) * m.z;
                 }
                 c.a_put4(slot, q, dv);
+                sched_fence();
             }
             c.a_end(slot);
-        }
+        });
+        X[12] = Hp;
     }
+    TCP_MARK(c, 2);
     // ---- phase C: dH = W1^T (s1 * g1) ----
     {
         const uint32_t tacc = c.acc_wait();
-#pragma unroll 1
-        for (int kb = 0; kb < NKB; ++kb) {
-            float g1[16];
-            tmem_ld16(tacc + kb * 32, g1);
+        TCP_MARK(c, 3);
+        float g0 = 0.f, g1s = 0.f, g2 = 0.f, g3 = 0.f;
+        for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int k = kb * 32 + c.hf * 16 + i;
                 const float4 w1 = lds4(rA + k * 8);
                 const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
-                const float d1 = fmaf(-a1, a1, 1.f) * g1[i];
-                X[17] = fmaf(w1.x, d1, X[17]);
-                X[18] = fmaf(w1.y, d1, X[18]);
-                X[19] = fmaf(w1.z, d1, X[19]);
-                X[20] = fmaf(w1.w, d1, X[20]);
+                if ((i & 3) == 3) sched_fence();
+                const float d1 = fmaf(-a1, a1, 1.f) * __uint_as_float(gr[i]);
+                g0 = fmaf(w1.x, d1, g0); g1s = fmaf(w1.y, d1, g1s); g2 = fmaf(w1.z, d1, g2); g3 = fmaf(w1.w, d1, g3);
             }
-        }
+        });
+        X[13] = g0; X[14] = g1s; X[15] = g2; X[16] = g3;
         tc_fence_before();
     }
+    TCP_MARK(c, 4);
     c.exchange(X);
-    Hval = X[16] + p.b3;
+    TCP_MARK(c, 5);
+    Hval = X[12] + p.b3;
     float S[4][4];
-    {
-        float Rp[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) Rp[e] = X[e];
-        tc_make_S(p, Rp, S);
-    }
+    tc_make_S(p, X, S);
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         float s = 0.f;
@@ -287,7 +361,7 @@ __device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const f
             float Rab = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) Rab = fmaf(S[a][k], S[b][k], Rab);
-            s = fmaf(p.Jm[a * 4 + b] - Rab, X[17 + b], s);
+            s = fmaf(p.Jm[a * 4 + b] - Rab, X[13 + b], s);
         }
         f[a] = s + p.Gv[a] * u;
     }
@@ -298,44 +372,28 @@ __device__ __noinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const f
 // product of H_net.  Product order: z2 -> acc0, g1 -> acc1, dz2 -> acc0, dg1 -> acc1.
 // ---------------------------------------------------------------------------------------
 template <class SH>
-__device__ __noinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u,
+__device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u,
                                          const float (&v)[4], float (&xbar)[4], float& ubar) {
     constexpr int NKB = SH::NKB;
     const float* rA = c.small() + SH::O_RA;
     const float* rB = c.small() + SH::O_RB;
     const float* rC = c.small() + SH::O_RC;
-    float Rp[16];
+    float Sp[12];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) Rp[i] = 0.f;
-    // ---- A1: a1 -> product 1 ; R_net forward partials ----
-#pragma unroll 1
-    for (int kb = 0; kb < NKB; ++kb) {
-        const int slot = c.a_begin();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float av[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = kb * 32 + c.hf * 16 + q * 4 + e;
-                const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
-                av[e] = tanh_acc(dot4(w1, y, m.x));
-                const float r = tanh_acc(dot4(lds4(rB + k * 4), y, m.w));
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 wc = lds4(rC + k * 16 + c4 * 4);
-                    Rp[c4 * 4 + 0] = fmaf(wc.x, r, Rp[c4 * 4 + 0]);
-                    Rp[c4 * 4 + 1] = fmaf(wc.y, r, Rp[c4 * 4 + 1]);
-                    Rp[c4 * 4 + 2] = fmaf(wc.z, r, Rp[c4 * 4 + 2]);
-                    Rp[c4 * 4 + 3] = fmaf(wc.w, r, Rp[c4 * 4 + 3]);
-                }
-            }
-            c.a_put4(slot, q, av);
-        }
-        c.a_end(slot);
-    }
-    c.exchange(Rp);
+    for (int i = 0; i < 12; ++i) Sp[i] = 0.f;
+    // ---- A1: a1 -> product 1 ; R_net forward sums ----
+    TCP_MARK(c, 15);
+#ifdef PHNN_TC_PROFILE
+    c.aphase = 2;
+#endif
+    tc_phase_a1<true>(c, y, Sp);
+#ifdef PHNN_TC_PROFILE
+    c.aphase = 3;
+#endif
+    TCP_MARK(c, 6);
+    c.exchange(Sp);
     float S[4][4], sv[4], w[4];
-    tc_make_S(p, Rp, S);
+    tc_make_S(p, Sp, S);
 #pragma unroll
     for (int a = 0; a < 4; ++a) sv[a] = fmaf(S[a][3], v[3], fmaf(S[a][2], v[2], fmaf(S[a][1], v[1], S[a][0] * v[0])));
 #pragma unroll
@@ -349,13 +407,11 @@ __device__ __noinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const f
     }
     // ---- B1: a2 (stashed), delta2 -> product 2 ----
     {
+        TCP_MARK(c, 5);
         const uint32_t tacc = c.acc_wait();
-#pragma unroll 1
-        for (int jb = 0; jb < NKB; ++jb) {
-            float z[16];
-            tmem_ld16(tacc + jb * 32, z);
+        TCP_MARK(c, 7);
+        for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&zr)[16]) {
             const int slot = c.a_begin();
-            float4* st = reinterpret_cast<float4*>(c.stash + ((size_t)(jb * 128 + c.row) * 32 + c.hf * 16));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float dv[4], a2v[4];
@@ -363,133 +419,174 @@ __device__ __noinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const f
                 for (int e = 0; e < 4; ++e) {
                     const int j = jb * 32 + c.hf * 16 + q * 4 + e;
                     const float4 m = lds4(rA + j * 8 + 4);
-                    const float a2 = tanh_acc(z[q * 4 + e] + m.y);
+                    const float a2 = tanh_acc(__uint_as_float(zr[q * 4 + e]) + m.y);
                     a2v[e] = a2;
                     dv[e] = fmaf(-a2, a2, 1.f) * m.z;
                 }
-                st[q] = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
+                *c.stash4(0, jb, q) = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
                 c.a_put4(slot, q, dv);
+                sched_fence();
+            }
+            c.a_end(slot);
+        });
+    }
+    TCP_MARK(c, 8);
+#ifdef PHNN_TC_PROFILE
+    c.aphase = 4;
+#endif
+    // ---- A3: da1 = s1 * (W1 w) -> product 3 (dz2 = W2 da1); a1 comes back from the stash ----
+    {
+        float4 an[4];
+        c.stash_load(1, 0, an);
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) {
+            float4 ac[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ac[q] = an[q];
+            if (kb + 1 < NKB) c.stash_load(1, kb + 1, an);
+            const int slot = c.a_begin();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
+                float av[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = kb * 32 + c.hf * 16 + q * 4 + e;
+                    av[e] = fmaf(-a1v[e], a1v[e], 1.f) * dot4(lds4(rA + k * 8), w, 0.f);
+                }
+                c.a_put4(slot, q, av);
             }
             c.a_end(slot);
         }
     }
-    // ---- A3: da1 = s1 * (W1 w) -> product 3 (dz2 = W2 da1) ----
-#pragma unroll 1
-    for (int kb = 0; kb < NKB; ++kb) {
-        const int slot = c.a_begin();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float av[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = kb * 32 + c.hf * 16 + q * 4 + e;
-                const float4 w1 = lds4(rA + k * 8);
-                const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
-                av[e] = fmaf(-a1, a1, 1.f) * dot4(w1, w, 0.f);
-            }
-            c.a_put4(slot, q, av);
-        }
-        c.a_end(slot);
-    }
+    TCP_MARK(c, 9);
     // ---- C2: g1 -> dH partial and the g1 half of xbar_H ----
     float Y[8];  // [0,4) dH partial, [4,8) xbar partial
 #pragma unroll
     for (int i = 0; i < 8; ++i) Y[i] = 0.f;
     {
+        float4 an[4];
+        c.stash_load(1, 0, an);
         const uint32_t tacc = c.acc_wait();
-#pragma unroll 1
-        for (int kb = 0; kb < NKB; ++kb) {
-            float g1[16];
-            tmem_ld16(tacc + kb * 32, g1);
+        TCP_MARK(c, 1);
+        for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
+            float4 ac[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = kb * 32 + c.hf * 16 + i;
-                const float4 w1 = lds4(rA + k * 8);
-                const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
-                const float s1 = fmaf(-a1, a1, 1.f);
-                const float da1 = s1 * dot4(w1, w, 0.f);
-                const float d1 = s1 * g1[i];
-                const float t = -2.f * a1 * da1 * g1[i];
-                Y[0] = fmaf(w1.x, d1, Y[0]); Y[1] = fmaf(w1.y, d1, Y[1]); Y[2] = fmaf(w1.z, d1, Y[2]); Y[3] = fmaf(w1.w, d1, Y[3]);
-                Y[4] = fmaf(w1.x, t, Y[4]); Y[5] = fmaf(w1.y, t, Y[5]); Y[6] = fmaf(w1.z, t, Y[6]); Y[7] = fmaf(w1.w, t, Y[7]);
+            for (int q = 0; q < 4; ++q) ac[q] = an[q];
+            if (kb + 1 < NKB) c.stash_load(1, kb + 1, an);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = kb * 32 + c.hf * 16 + q * 4 + e;
+                    const float4 w1 = lds4(rA + k * 8);
+                    const float a1 = a1v[e];
+                    const float s1 = fmaf(-a1, a1, 1.f);
+                    const float g1 = __uint_as_float(gr[q * 4 + e]);
+                    const float d1 = s1 * g1;
+                    const float t = -2.f * a1 * (s1 * dot4(w1, w, 0.f)) * g1;
+                    Y[0] = fmaf(w1.x, d1, Y[0]); Y[1] = fmaf(w1.y, d1, Y[1]); Y[2] = fmaf(w1.z, d1, Y[2]); Y[3] = fmaf(w1.w, d1, Y[3]);
+                    Y[4] = fmaf(w1.x, t, Y[4]); Y[5] = fmaf(w1.y, t, Y[5]); Y[6] = fmaf(w1.z, t, Y[6]); Y[7] = fmaf(w1.w, t, Y[7]);
+                }
             }
-        }
+        });
     }
+    TCP_MARK(c, 10);
+#ifdef PHNN_TC_PROFILE
+    c.aphase = 5;
+#endif
     // ---- B3: e2 = -2 a2 da2 w3 -> product 4 (dg1 = W2^T e2) ----
     {
         const uint32_t tacc = c.acc_wait();
-#pragma unroll 1
-        for (int jb = 0; jb < NKB; ++jb) {
-            float dz[16];
-            tmem_ld16(tacc + jb * 32, dz);
+        TCP_MARK(c, 3);
+        float4 an[4];
+        c.stash_load(0, 0, an);
+        for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&dz)[16]) {
+            float4 a2q[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a2q[q] = an[q];
+            if (jb + 1 < NKB) c.stash_load(0, jb + 1, an);
             const int slot = c.a_begin();
-            const float4* st = reinterpret_cast<const float4*>(c.stash + ((size_t)(jb * 128 + c.row) * 32 + c.hf * 16));
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 a2q = st[q];
-                const float a2v[4] = {a2q.x, a2q.y, a2q.z, a2q.w};
+                const float a2v[4] = {a2q[q].x, a2q[q].y, a2q[q].z, a2q[q].w};
                 float ev[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = jb * 32 + c.hf * 16 + q * 4 + e;
                     const float w3 = rA[j * 8 + 6];
-                    const float da2 = fmaf(-a2v[e], a2v[e], 1.f) * dz[q * 4 + e];
+                    const float da2 = fmaf(-a2v[e], a2v[e], 1.f) * __uint_as_float(dz[q * 4 + e]);
                     ev[e] = -2.f * a2v[e] * da2 * w3;
                 }
                 c.a_put4(slot, q, ev);
             }
             c.a_end(slot);
-        }
+        });
     }
+    TCP_MARK(c, 11);
     // ---- while product 4 runs: dH total, then the R_net chain (thread-local over my hidden units) ----
     float G4[4] = {Y[0], Y[1], Y[2], Y[3]};
     c.exchange(G4);
     float X4[4] = {Y[4], Y[5], Y[6], Y[7]};
     {
-        float tg[4], Rb[16];
+        // cotangent of S: -(v t^T + g s^T) symmetrised, packed with multiplicity 2 off the diagonal
+        float tg[4], Rb[12];
 #pragma unroll
         for (int a = 0; a < 4; ++a) tg[a] = fmaf(S[a][3], G4[3], fmaf(S[a][2], G4[2], fmaf(S[a][1], G4[1], S[a][0] * G4[0])));
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) Rb[a * 4 + b] = -0.5f * (v[a] * tg[b] + G4[a] * sv[b] + v[b] * tg[a] + G4[b] * sv[a]);
+            for (int b = a; b < 4; ++b)
+                Rb[sym_idx(a, b)] = (a == b ? -0.5f : -1.0f) * (v[a] * tg[b] + G4[a] * sv[b] + v[b] * tg[a] + G4[b] * sv[a]);
+        Rb[10] = 0.f; Rb[11] = 0.f;
 #pragma unroll 1
-        for (int kk = 0; kk < SH::HID / 2; ++kk) {
-            const int k = (kk >> 4) * 32 + c.hf * 16 + (kk & 15);
-            float rb = 0.f;
+        for (int kk = 0; kk < SH::HID / 2; kk += 4) {
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 wc = lds4(rC + k * 16 + c4 * 4);
-                rb = fmaf(wc.x, Rb[c4 * 4 + 0], rb);
-                rb = fmaf(wc.y, Rb[c4 * 4 + 1], rb);
-                rb = fmaf(wc.z, Rb[c4 * 4 + 2], rb);
-                rb = fmaf(wc.w, Rb[c4 * 4 + 3], rb);
+            for (int e = 0; e < 4; ++e) {
+                const int k = ((kk + e) >> 4) * 32 + c.hf * 16 + ((kk + e) & 15);
+                const float4 c0 = lds4(rC + k * 12), c1 = lds4(rC + k * 12 + 4);
+                const float2 c2 = *reinterpret_cast<const float2*>(rC + k * 12 + 8);
+                float rb = c0.x * Rb[0];
+                rb = fmaf(c0.y, Rb[1], rb); rb = fmaf(c0.z, Rb[2], rb); rb = fmaf(c0.w, Rb[3], rb);
+                rb = fmaf(c1.x, Rb[4], rb); rb = fmaf(c1.y, Rb[5], rb); rb = fmaf(c1.z, Rb[6], rb); rb = fmaf(c1.w, Rb[7], rb);
+                rb = fmaf(c2.x, Rb[8], rb); rb = fmaf(c2.y, Rb[9], rb);
+                const float4 wr = lds4(rB + k * 4);
+                const float r1 = tanh_acc(dot4(wr, y, rA[k * 8 + 7]));
+                const float zb = rb * fmaf(-r1, r1, 1.f);
+                X4[0] = fmaf(wr.x, zb, X4[0]); X4[1] = fmaf(wr.y, zb, X4[1]); X4[2] = fmaf(wr.z, zb, X4[2]); X4[3] = fmaf(wr.w, zb, X4[3]);
             }
-            const float4 wr = lds4(rB + k * 4);
-            const float r1 = tanh_acc(dot4(wr, y, rA[k * 8 + 7]));
-            const float zb = rb * fmaf(-r1, r1, 1.f);
-            X4[0] = fmaf(wr.x, zb, X4[0]); X4[1] = fmaf(wr.y, zb, X4[1]); X4[2] = fmaf(wr.z, zb, X4[2]); X4[3] = fmaf(wr.w, zb, X4[3]);
         }
     }
+    TCP_MARK(c, 12);
     // ---- C4: the dg1 half of xbar_H ----
     {
         const uint32_t tacc = c.acc_wait();
-#pragma unroll 1
-        for (int kb = 0; kb < NKB; ++kb) {
-            float dg[16];
-            tmem_ld16(tacc + kb * 32, dg);
+        TCP_MARK(c, 13);
+        float4 an[4];
+        c.stash_load(1, 0, an);
+        for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&dg)[16]) {
+            float4 ac[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = kb * 32 + c.hf * 16 + i;
-                const float4 w1 = lds4(rA + k * 8);
-                const float a1 = tanh_acc(dot4(w1, y, rA[k * 8 + 4]));
-                const float t = fmaf(-a1, a1, 1.f) * dg[i];
-                X4[0] = fmaf(w1.x, t, X4[0]); X4[1] = fmaf(w1.y, t, X4[1]); X4[2] = fmaf(w1.z, t, X4[2]); X4[3] = fmaf(w1.w, t, X4[3]);
+            for (int q = 0; q < 4; ++q) ac[q] = an[q];
+            if (kb + 1 < NKB) c.stash_load(1, kb + 1, an);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = kb * 32 + c.hf * 16 + q * 4 + e;
+                    const float4 w1 = lds4(rA + k * 8);
+                    const float t = fmaf(-a1v[e], a1v[e], 1.f) * __uint_as_float(dg[q * 4 + e]);
+                    X4[0] = fmaf(w1.x, t, X4[0]); X4[1] = fmaf(w1.y, t, X4[1]); X4[2] = fmaf(w1.z, t, X4[2]); X4[3] = fmaf(w1.w, t, X4[3]);
+                }
             }
-        }
+        });
         tc_fence_before();
     }
+    TCP_MARK(c, 14);
     c.exchange(X4);
+    TCP_MARK(c, 5);
 #pragma unroll
     for (int i = 0; i < 4; ++i) xbar[i] = X4[i];
     ubar = fmaf(p.Gv[3], v[3], fmaf(p.Gv[2], v[2], fmaf(p.Gv[1], v[1], p.Gv[0] * v[0])));
@@ -555,11 +652,24 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         c.qdone = 0;
         c.split = split;
         c.store = (c.hf == 0);
-        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, 128, HID);
+        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, 128, TcCtx<SH>::WS_EXTRA);
         c.stash = p.ws ? p.ws + (size_t)blockIdx.x * tile_floats + ws_floats_per_tile(NS, p.T, p.S, 128, 0) : nullptr;
         mbar_wait(&bars[SH::B_SMALL], 0);
+#ifdef PHNN_TC_PROFILE
+        for (int i = 0; i < 16; ++i) c.prof[i] = 0;
+        for (int i = 0; i < 8; ++i) c.await[i] = 0;
+        c.aphase = 0;
+        c.tlast = clock64();
+#endif
         run_job(c, p, (long long)blockIdx.x, c.row, n_outer);
         tc_fence_before();
+#ifdef PHNN_TC_PROFILE
+        if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 255) && p.dbg)
+        {
+            for (int i = 0; i < 16; ++i) p.dbg[(threadIdx.x ? 16 : 0) + i] = c.prof[i];
+            if (threadIdx.x == 0) for (int i = 0; i < 8; ++i) p.dbg[32 + i] = c.await[i];
+        }
+#endif
     } else if (warp == 8) {
         // ===== MMA issuer =====
         if (lane == 0) {
@@ -572,10 +682,10 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
 #pragma unroll 1
                 for (int kb = 0; kb < SH::NKB; ++kb) {
                     const uint32_t slot = ablk & 1u;
-                    mbar_wait(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u);
+                    mbar_wait_sleep(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u, 32);
                     const uint32_t a_hi = a_base + (slot * 2) * SH::A_TILE, a_lo = a_hi + SH::A_TILE;
                     uint32_t e = bent % SH::NBE;
-                    mbar_wait(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
+                    mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, 32);
                     tc_fence_after();
                     uint32_t b_t = b_base + e * SH::B_TILE;
 #pragma unroll
@@ -590,7 +700,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                     ++bent;
                     if (split == 3) {
                         e = bent % SH::NBE;
-                        mbar_wait(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
+                        mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, 32);
                         tc_fence_after();
                         b_t = b_base + e * SH::B_TILE;
 #pragma unroll
@@ -618,7 +728,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                 for (int kb = 0; kb < SH::NKB; ++kb) {
                     for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
                         const uint32_t e = bent % SH::NBE;
-                        mbar_wait(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u);
+                        mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, 128);
                         mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
                         bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)(kb * 2 + hl) * SH::B_TILE, SH::B_TILE,
                                  &bars[SH::B_BFULL + e]);

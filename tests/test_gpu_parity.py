@@ -215,3 +215,108 @@ def test_unknown_integrator_raises(env):
     z, sd, pk = get("cartpole_h128")
     with pytest.raises(ValueError):
         ops.rollout(pk.handle, cu(z["rand_x"]), torch.zeros(32, 3, 1, device="cuda"), 0.02, 7, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 / TMEM kernel (cart-pole pHNN, hidden 128 and 256).  tensor_mode 3 = 3xTF32 error
+# compensation and must meet the SAME FP32 tolerances as the FP32-FMA kernel; tensor_mode 1 =
+# plain TF32, stated looser tolerance (TF32 operand rounding, SURVEY.md fact 10: ~4e-5 rollout,
+# ~4e-4 dJ/dU): 2e-4 cost/rollout, 1e-3 gradient, controls 0.05*lr.
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def tc_env(env):
+    from phnn_mpc_b200.packing import PackedModel
+    ops, get = env
+    packs = {}
+
+    def get_tc(name, mode):
+        key = (name, mode)
+        if key not in packs:
+            z, sd = load_golden(name)
+            pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, "phnn")
+            pk.set_option("tensor_min_batch", 0)
+            pk.set_option("tensor_mode", mode)
+            assert pk.get_option("tensor_mode") == mode
+            packs[key] = (z, sd, pk)
+        return packs[key]
+
+    return ops, get_tc
+
+
+@pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256"])
+@pytest.mark.parametrize("mode", [3, 1])
+def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
+    ops, get_tc = tc_env
+    z, sd, pk = get_tc(name, mode)
+    step_tol, hor_tol, grad_tol, u_fac = (STEP_TOL, HORIZON_TOL, HORIZON_TOL, 0.02) if mode == 3 else (2e-3, 2e-4, 1e-3, 0.05)
+    dx, H = ops.forward(pk.handle, cu(z["rand_x"]), cu(z["rand_u"]))
+    assert rel_err(dx.cpu().numpy(), z["rand_dx"]) < step_tol
+    assert rel_err(H.cpu().numpy(), z["rand_H"]) < step_tol
+    ca = cost_args(z)
+    dt, lr = float(z["mpc_dt"]), float(z["mpc_lr"])
+    lo, hi = [float(v) for v in z["mpc_bounds"]]
+    for integ, iid in (("euler", 0), ("rk4", 1)):
+        p = "mpc_%s_" % integ
+        tr, _ = ops.rollout(pk.handle, cu(z["mpc_x0"]), cu(np.clip(z["mpc_U0"], lo, hi)), dt, iid, 0)
+        assert rel_err(tr.cpu().numpy(), z[p + "traj0"]) < hor_tol
+        cost, g, tr2 = ops.cost_grad(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, True, True)
+        assert rel_err(cost.cpu().numpy(), z[p + "hist"][0]) < hor_tol
+        assert rel_err(g.cpu().numpy(), z[p + "grad0"]) < grad_tol
+        assert rel_err(tr2.cpu().numpy(), z[p + "traj0"]) < hor_tol
+        out = (z["mpc_U0"] < lo) | (z["mpc_U0"] > hi)
+        assert np.all(g.cpu().numpy()[out] == 0)
+        iters = z[p + "hist"].shape[0]
+        for rmode, key in ((0, "U_last"), (1, "U_best")):
+            U, hist, best = ops.mpc_solve(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, lr, 0.9, 0.999, 1e-8,
+                                          iters, rmode, True)
+            assert rel_err(hist.cpu().numpy(), z[p + "hist"]) < hor_tol
+            assert np.abs(U.cpu().numpy() - z[p + key]).max() < u_fac * lr + 1e-5
+            assert rel_err(best.cpu().numpy(), z[p + "best"]) < hor_tol
+
+
+@pytest.mark.parametrize("B", [1, 127, 129, 700])
+def test_tc_ragged_tiles_vs_oracle(tc_env, B):
+    """partially filled 128-instance tiles, energies in both orderings, against the CPU oracle"""
+    from oracle.phnn_oracle import OracleModel
+    ops, get_tc = tc_env
+    z, sd, pk = get_tc("cartpole_h256", 3)
+    M = OracleModel(sd, "phnn")
+    rng = np.random.default_rng(B)
+    x = (rng.uniform(-1, 1, size=(B, 4)) * [1.0, 0.3, 0.5, 0.5]).astype(np.float32)
+    U = rng.uniform(-5, 5, size=(B, 6, 1)).astype(np.float32)
+    dx, H = ops.forward(pk.handle, cu(x), cu(U[:, 0]))
+    dxo, Ho = M.forward(x, U[:, 0])
+    # H is a cancelling sum of O(1) terms: normalise by at least 1 (a single tiny |H| would inflate rel_err)
+    assert rel_err(dx.cpu().numpy(), dxo) < STEP_TOL
+    assert np.abs(H.cpu().numpy() - Ho).max() < STEP_TOL * max(1.0, np.abs(Ho).max())
+    for emode in (1, 2):
+        tr, en = ops.rollout(pk.handle, cu(x), cu(U), 0.02, 1, emode)
+        tro, eno = M.rollout(x, U, 0.02, "rk4", energy_mode=emode)
+        assert rel_err(tr.cpu().numpy(), tro) < HORIZON_TOL and rel_err(en.cpu().numpy(), eno) < HORIZON_TOL
+
+
+def test_tc_matches_fp32_kernel_and_oracle_cfg4_shape(tc_env, env):
+    """BASELINE cfg4-shaped work (h=256, H=50, RK4) on 256 instances: tcgen05 kernel vs the CPU oracle and
+    vs the FP32-FMA kernel."""
+    from oracle.phnn_oracle import OracleModel
+    ops, get_tc = tc_env
+    _, get = env
+    z, sd, pk_tc = get_tc("cartpole_h256", 3)
+    _, _, pk_fp = get("cartpole_h256")
+    M = OracleModel(sd, "phnn")
+    B, H, iters = 256, 50, 3
+    g = torch.Generator().manual_seed(11)
+    x0 = ((torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])).numpy()
+    Q = np.diag([10.0, 200.0, 1.0, 10.0]).astype(np.float32)
+    R = np.array([[0.01]], np.float32)
+    ca = (torch.from_numpy(Q), torch.from_numpy(R), torch.zeros(4), True, -15.0, 15.0, None, None, 1000.0)
+    U0 = np.zeros((B, H, 1), np.float32)
+    C = M.cost_struct(Q, R, np.zeros(4), -15.0, 15.0)
+    Uo, histo, _ = M.mpc_solve(C, x0, U0, 0.02, "rk4", lr=0.015, iters=iters)
+    outs = []
+    for pk in (pk_tc, pk_fp):
+        U, hist, _ = ops.mpc_solve(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, 0.015, 0.9, 0.999, 1e-8, iters, 0, True)
+        assert rel_err(hist.cpu().numpy(), histo) < HORIZON_TOL
+        assert np.abs(U.cpu().numpy() - Uo).max() < 0.02 * 0.015 + 1e-5
+        outs.append(U.cpu().numpy())
+    assert np.abs(outs[0] - outs[1]).max() < 0.02 * 0.015 + 1e-5
