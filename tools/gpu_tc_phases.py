@@ -32,3 +32,5 @@ for i, n in enumerate(names):
     print("  %-18s thread0 %8.0f   thread255 %8.0f   cycles/pair" % (n, d[0, i] / npair, d[1, i] / npair))
 print("  total              thread0 %8.0f" % (d[0].sum() / npair))
 print("  a_begin waits per pair: fwdA %.0f fwdB %.0f adjA1 %.0f adjB1 %.0f adjA3 %.0f adjB3 %.0f" % tuple(aw[:6] / npair))
+sb = dbg.cpu().numpy()[40:44]
+print("  a_end per pair: fences %.0f, syncwarp+arrive %.0f  (48 blocks per pair)" % (sb[0] / npair, sb[1] / npair))
