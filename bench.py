@@ -309,6 +309,13 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     fp32_peak = fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    L.phnn_tf32_probe(ctypes.c_void_p(probe_out.data_ptr()), 2048, 148, st, ctypes.byref(fl))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.phnn_tf32_probe(ctypes.c_void_p(probe_out.data_ptr()), 16384, 148, st, ctypes.byref(fl))
+    e1.record()
+    torch.cuda.synchronize()
+    tf32_peak = fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
     algo = solve_flops(kind, h, 4, H, iters, S) * B
     kernel_ms = float(np.mean(step_ms))
     achieved = algo / (kernel_ms * 1e-3) / 1e12
@@ -342,8 +349,8 @@ def main():
                         "3xTF32 error-compensated" if split == 3 else "plain TF32"),
                     "kernel_ms": kernel_ms,
                     "executed_tensor_tflops": mma_flops / (kernel_ms * 1e-3) / 1e12,
-                    "tf32_dense_peak_tflops": bf16_peak / 2,
-                    "tensor_pipe_frac": mma_flops / (kernel_ms * 1e-3) / 1e12 / (bf16_peak / 2),
+                    "tf32_mma_peak_tflops": tf32_peak,
+                    "tensor_pipe_frac": mma_flops / (kernel_ms * 1e-3) / 1e12 / tf32_peak,
                     "executed_over_algorithmic": mma_flops / algo,
                     "fp32_fma_peak_tflops": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak,
                     "note": "FP32-level accuracy on TF32 tensor cores costs 3 MMAs per product at half the bf16 rate, and the "

@@ -126,6 +126,9 @@ int phnn_mpc_solve(const phnn_pack *pack, const phnn_cost_desc *cost_desc, const
  * x 256 threads and returns the FLOPs it executes in *flops; bench.py times it with CUDA events
  * to get this GPU's sustained FP32-FMA rate, the roofline denominator of the FP32 path.        */
 int phnn_ffma_probe(float *d_out, int iters, int blocks, void *stream, double *flops);
+/* Same for the TF32 tcgen05.mma issue rate (n_mma 128x256x8 MMAs per CTA on resident operands): the
+ * tensor-pipe denominator bench.py reports beside the bf16 peak of MEASURED_PEAKS.json.            */
+int phnn_tf32_probe(float *d_out, int n_mma, int blocks, void *stream, double *flops);
 
 #ifdef __cplusplus
 }

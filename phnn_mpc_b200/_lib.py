@@ -64,6 +64,8 @@ def lib():
     L.phnn_pack_get_option.restype = ll
     L.phnn_ffma_probe.argtypes = [vp, ci, ci, vp, ctypes.POINTER(cd)]
     L.phnn_ffma_probe.restype = ci
+    L.phnn_tf32_probe.argtypes = [vp, ci, ci, vp, ctypes.POINTER(cd)]
+    L.phnn_tf32_probe.restype = ci
     for f in ("phnn_pack_create", "phnn_pack_destroy", "phnn_pack_dims", "phnn_forward", "phnn_vjp", "phnn_rollout",
               "phnn_cost_grad", "phnn_mpc_solve"):
         getattr(L, f).restype = ci
@@ -72,7 +74,7 @@ def lib():
 
 
 EXPORTS = ["phnn_last_error", "phnn_version", "phnn_pack_create", "phnn_pack_destroy", "phnn_pack_dims",
-           "phnn_forward", "phnn_vjp", "phnn_rollout", "phnn_workspace_bytes", "phnn_cost_grad", "phnn_mpc_solve", "phnn_ffma_probe",
+           "phnn_forward", "phnn_vjp", "phnn_rollout", "phnn_workspace_bytes", "phnn_cost_grad", "phnn_mpc_solve", "phnn_ffma_probe", "phnn_tf32_probe",
            "phnn_pack_set_option", "phnn_pack_get_option"]
 
 

@@ -490,3 +490,53 @@ extern "C" int phnn_ffma_probe(float* d_out, int iters, int blocks, void* stream
     if (flops) *flops = 2.0 * 16.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
     return 0;
 }
+
+// ---- measurement utility: TF32 tcgen05.mma issue rate of this GPU (128x256x8 MMAs back to back on
+// resident operands, all SMs); bench.py uses it as the tensor-pipe denominator of the 3xTF32 kernel ----
+__global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int n_mma, float* sink) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 128);
+    float* A = reinterpret_cast<float*>(phnn_smem + 1024);  // 128 x 32 tf32 (16 KB) then 256 x 32 (32 KB)
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) A[i] = 0.001f * (float)(i & 255);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_ptr;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a = smem_u32(phnn_smem + 1024), b = a + 16384;
+        uint32_t ph = 0;
+        for (int i = 0; i < n_mma; i += 64) {
+            for (int j = 0; j < 64; ++j)
+                umma_tf32(tbase + (j & 1) * 256, umma_desc_sw128(a + (j & 3) * 32), umma_desc_sw128(b + (j & 3) * 32), idesc, 1u);
+            umma_commit(&bars[0]);
+            mbar_wait(&bars[0], ph);
+            ph ^= 1;
+        }
+        if (sink && n_mma < 0) sink[0] = 1.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
+}
+
+extern "C" int phnn_tf32_probe(float* d_out, int n_mma, int blocks, void* stream, double* flops) {
+    if (!d_out || n_mma <= 0 || blocks <= 0) return fail(PHNN_E_ARG, "phnn_tf32_probe: bad argument");
+    const int smem = 1024 + 16384 + 32768;
+    CUDA_TRY(cudaFuncSetAttribute(tf32_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    n_mma = (n_mma + 63) / 64 * 64;
+    tf32_probe_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(n_mma, d_out);
+    CUDA_TRY(cudaGetLastError());
+    if (flops) *flops = 2.0 * 128.0 * 256.0 * 8.0 * (double)n_mma * (double)blocks;
+    return 0;
+}

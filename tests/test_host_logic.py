@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     from phnn_mpc_b200.build import build_library
     lib = ctypes.CDLL(build_library())
     header = open(os.path.join(REPO, "include", "phnn_mpc.h")).read()
-    declared = set(re.findall(r"\b(phnn_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(phnn_[a-z0-9_]+)\s*\(", header))
     declared -= {"phnn_model_desc", "phnn_cost_desc", "phnn_pack"}
     assert len(declared) >= 11
     for sym in declared:
