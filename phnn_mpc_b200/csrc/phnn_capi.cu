@@ -316,7 +316,18 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     P.tc_split = pk->tc_mode == 1 ? 1 : 3;
     P.ng = 1;
     P.dbg = g_dbg;
-    kern<<<(unsigned)tiles, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
+    P.tiles = tiles;
+    P.sched = nullptr;
+    long long grid = tiles;
+    if (P.mode == MODE_SOLVE && P.iters > 0 && P.ws) {
+        // work-stealing solve: persistent CTAs pull (tile, iteration) units; the scheduler words sit after the
+        // per-tile regions of the workspace and are zeroed on the stream before the launch
+        const size_t tile_floats = ws_floats_per_tile(SH::NS, P.T, P.S, SH::TM, 2 * SH::HID);
+        P.sched = reinterpret_cast<int*>(P.ws + (size_t)tiles * tile_floats);
+        CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
+        if (grid > pk->num_sms) grid = pk->num_sms;
+    }
+    kern<<<(unsigned)grid, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -420,7 +431,8 @@ extern "C" size_t phnn_workspace_bytes(const phnn_pack* pk, long B, int T, int i
     if (!pk || B <= 0 || T <= 0) return 0;
     // sized for 128-instance tiles (the tcgen05 kernel); a superset of what 32-instance tiles need
     const size_t tiles = ((size_t)B + 127) / 128;
-    return tiles * ws_floats_per_tile(pk->n, T, integrator == PHNN_RK4 ? 4 : 1, 128, 2 * pk->h) * sizeof(float);
+    return tiles * ws_floats_per_tile(pk->n, T, integrator == PHNN_RK4 ? 4 : 1, 128, 2 * pk->h) * sizeof(float) +
+           sizeof(int) * (tiles + 4);  // + the work-stealing scheduler words
 }
 
 extern "C" int phnn_cost_grad(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, const float* U,

@@ -113,6 +113,8 @@ struct KParams {
     float* dJdU;       // COSTGRAD [B,T] (nullable)
     float* cost_hist;  // SOLVE [iters,B] (nullable)
     float* ws;         // workspace
+    int* sched;        // work-stealing solve (tcgen05 kernel): [0] unit counter, [1 + tile] iterations completed
+    long long tiles;   // number of 128-instance tiles (work-stealing solve)
     long long* dbg;    // optional profiling output (PHNN_TC_PROFILE builds)
 };
 
@@ -120,8 +122,35 @@ struct KParams {
 // controls [T][TW] (lane-interleaved so the accesses of a warp coalesce)
 // (+ `extra` floats per instance: the tcgen05 kernel stashes one hidden-layer activation there)
 __host__ __device__ inline size_t ws_floats_per_tile(int NS, int T, int S, int TW, int extra = 0) {
-    return (size_t)TW * ((size_t)T * S * NS + 3 * (size_t)T + (size_t)extra);
+    return (size_t)TW * ((size_t)T * S * NS + 3 * (size_t)T + 1 + (size_t)extra);
 }
+
+// One unit of work of a job: iteration `it` (1-based) of tile `tile`.  The static schedule hands a
+// CTA the iterations of its own tile in order; the work-stealing schedule of the tcgen05 kernel
+// hands out (tile, iteration) pairs from a global counter so that batches whose tile count is not
+// a multiple of the SM count do not idle SMs in the last wave.
+struct Unit {
+    long long tile;
+    int it;
+};
+struct StaticSched {
+    long long tile;
+    int n_outer, it;
+    __device__ __forceinline__ bool next(Unit& u) {
+        if (it >= n_outer) return false;
+        u.tile = tile;
+        u.it = ++it;
+        return true;
+    }
+    template <class ENG>
+    __device__ __forceinline__ void done(ENG& c, const Unit&) {
+        // the storing thread's update of U[.,0] must be visible to the instance's other owners
+        // before they re-read it at the top of the next forward sweep
+        c.gbar();
+    }
+    static constexpr bool kStateInWorkspace = false;
+    __device__ __forceinline__ long long tile0() const { return tile; }
+};
 
 // ---------------------------------------------------------------------------------------
 // PTX helpers: mbarrier, bulk copy, named barriers, MUFU
@@ -257,6 +286,7 @@ struct Ctx {
     // hidden unit handled in micro-tile column o
     __device__ __forceinline__ int kown(int o) const { return wcol + ((o >> 2) << 5) + (o & 3); }
     __device__ __forceinline__ float* row_own(float* buf, int k) const { return buf + k * GI + (chunk << 3); }
+    __device__ __forceinline__ void begin_unit(const KParams&, long long) {}
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
         phnn::eval_fwd(*this, p, y, u, f, H);
     }
@@ -930,10 +960,16 @@ __device__ __forceinline__ float clampu(const KParams& p, float u) {
 // co-owning threads performs the global stores).  tile/slot locate the instance and its
 // lane-interleaved workspace.
 // ---------------------------------------------------------------------------------------
-template <class ENG>
-__device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long long tile, const int slot,
-                                        const int n_outer) {
+template <class ENG, class SCHED>
+__device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, const int slot) {
     constexpr int NS = ENG::NS, TW = ENG::TW;
+    Unit unit;
+    float best_reg = __int_as_float(0x7f800000);
+#pragma unroll 1
+  while (sched.next(unit)) {
+    const long long tile = unit.tile;
+    const int it = unit.it;
+    c.begin_unit(p, tile);
     const long long b = tile * TW + slot;  // my instance
     const bool valid = b < p.B;
     const bool st = valid && c.store;
@@ -950,6 +986,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
     float* adam_m = wsg ? wsg + (size_t)E * NS * TW : nullptr;
     float* adam_v = adam_m ? adam_m + (size_t)T * TW : nullptr;
     float* ubest = adam_v ? adam_v + (size_t)T * TW : nullptr;
+    float* bestws = ubest ? ubest + (size_t)T * TW : nullptr;
     const bool solve = (p.mode == MODE_SOLVE);
     const bool one_vjp = (p.mode == MODE_VJP);
     const bool need_adj = solve || one_vjp || (p.mode == MODE_COSTGRAD && p.want_grad);
@@ -958,17 +995,17 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
     // rollout_trajectory's energy list needs one more evaluation, at y_T (src/integrators.py:184)
     const int t_end = one_vjp ? 0 : T + ((p.mode == MODE_ROLLOUT && p.energy_mode == 2) ? 1 : 0);
 
-    if (solve && st) {
+    if (solve && st && it == 1) {
         for (int t = 0; t < T; ++t) {
             adam_m[t * TW + slot] = 0.f;
             adam_v[t * TW + slot] = 0.f;
             ubest[t * TW + slot] = clampu(p, p.U[b * T + t]);
         }
     }
-    float best = __int_as_float(0x7f800000);
+    float best = best_reg;
+    if (SCHED::kStateInWorkspace) best = (it == 1 || !valid) ? __int_as_float(0x7f800000) : __ldcg(bestws + slot);
 
-#pragma unroll 1
-    for (int it = 1; it <= n_outer; ++it) {
+    {
         // ---------------- forward sweep ----------------
         float x[NS];
 #pragma unroll
@@ -1123,7 +1160,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
                 if (st) p.dJdU[b * T + t] = g;
             } else if (st) {
                 if (improved) ubest[t * TW + slot] = u;
-                float m = adam_m[t * TW + slot], vv = adam_v[t * TW + slot];
+                float m = __ldcg(adam_m + t * TW + slot), vv = __ldcg(adam_v + t * TW + slot);
                 m = m + w1 * (g - m);
                 vv = vv * b2f + w2 * g * g;
                 adam_m[t * TW + slot] = m;
@@ -1132,15 +1169,25 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, const long lon
                 p.U[b * T + t] = uraw + (-step_size * m) / den;
             }
         }
-        // the storing thread's update of U[.,0] must be visible to the instance's other owners
-        // before they re-read it at the top of the next forward sweep
-        c.gbar();
+        best_reg = best;
+        if (SCHED::kStateInWorkspace && st) bestws[slot] = best;
     }
-    if (solve && st) {
+    if (solve && st && it == p.iters) {
         for (int t = 0; t < T; ++t)
-            p.U[b * T + t] = (p.return_mode == 0) ? clampu(p, __ldcg(p.U + b * T + t)) : ubest[t * TW + slot];
+            p.U[b * T + t] = (p.return_mode == 0) ? clampu(p, __ldcg(p.U + b * T + t)) : __ldcg(ubest + t * TW + slot);
         if (p.cost) p.cost[b] = best;
     }
+    sched.done(c, unit);
+  }
+  // a solve with zero iterations still clamps / copies the initial guess (src/mpc_controller.py:203-207)
+  if (p.mode == MODE_SOLVE && p.iters == 0) {
+      const long long tile0 = sched.tile0();
+      const long long b = tile0 * TW + slot;
+      if (tile0 >= 0 && b < p.B && c.store) {
+          for (int t = 0; t < p.T; ++t) p.U[b * p.T + t] = clampu(p, p.U[b * p.T + t]);
+          if (p.cost) p.cost[b] = __int_as_float(0x7f800000);
+      }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1223,7 +1270,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) phnn_kernel(const __grid_const
     c.goff = SH::SMALL + SH::RING + grp * SH::G_FLOATS;
     mbar_wait(&bars[2 * NST], 0);  // small weights landed
 
-    run_job(c, p, (long long)blockIdx.x * p.ng + grp, lane, n_outer);
+    StaticSched sched{(long long)blockIdx.x * p.ng + grp, n_outer, 0};
+    run_job(c, p, sched, lane);
 }
 
 }  // namespace phnn

@@ -251,6 +251,10 @@ struct TcCtx {
         for (int i = 0; i < N; ++i) v[i] += x[i * 256 + (t ^ 128)];
         gbar();
     }
+    __device__ __forceinline__ void begin_unit(const KParams& p, long long tile) {
+        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, TW, WS_EXTRA);
+        stash = p.ws ? p.ws + (size_t)tile * tile_floats + ws_floats_per_tile(NS, p.T, p.S, TW, 0) : nullptr;
+    }
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[4], float u, float (&f)[4], float& H) {
         tc_eval_fwd(*this, p, y, u, f, H);
     }
@@ -620,6 +624,54 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     ubar = fmaf(p.Gv[3], v[3], fmaf(p.Gv[2], v[2], fmaf(p.Gv[1], v[1], p.Gv[0] * v[0])));
 }
 
+// Work-stealing schedule of the solve: (tile, iteration) units from a global counter.  All per-instance
+// state that crosses iterations (U, Adam moments, best controls, best cost) lives in global memory and is
+// read with ld.cg, so any CTA can run any iteration of any tile once the previous iteration of that tile
+// has been published.  next() is called by all 320 threads of the CTA (it contains CTA barriers).
+struct StealSched {
+    int* counter;
+    int* progress;
+    long long tiles;
+    int iters;
+    int* slot;  // shared-memory broadcast slot
+    static constexpr bool kStateInWorkspace = true;
+    __device__ __forceinline__ long long tile0() const { return -1; }
+    __device__ __forceinline__ int grab() {
+        if (threadIdx.x == 0) {
+            const int n = atomicAdd(counter, 1);
+            const long long total = tiles * iters;
+            if (n < total) {
+                const int it = (int)(n / tiles) + 1;
+                const long long tile = n % tiles;
+                if (it > 1) {
+                    while (*reinterpret_cast<volatile int*>(progress + tile) < it - 1) __nanosleep(256);
+                    __threadfence();
+                }
+            }
+            *slot = n < total ? n : -1;
+        }
+        __syncthreads();
+        const int n = *slot;
+        __syncthreads();
+        return n;
+    }
+    __device__ __forceinline__ bool next(Unit& u) {
+        const int n = grab();
+        if (n < 0) return false;
+        u.it = (int)(n / tiles) + 1;
+        u.tile = n % tiles;
+        return true;
+    }
+    template <class ENG>
+    __device__ __forceinline__ void done(ENG&, const Unit& u) {
+        group_bar(6, 256);  // all element threads have issued their global writes of this unit
+        if (threadIdx.x == 0) {
+            __threadfence();
+            *reinterpret_cast<volatile int*>(progress + u.tile) = u.it;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
@@ -665,8 +717,11 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         case MODE_COSTGRAD: nfwd = E; nadj = p.want_grad ? E : 0; break;
         default: n_outer = p.iters; nfwd = E; nadj = E; break;
     }
-    const long long nprod = (long long)n_outer * (2LL * nfwd + 4LL * nadj);
+    const bool steal = (p.mode == MODE_SOLVE) && p.sched != nullptr && p.iters > 0;
+    // products per schedule unit: a whole job (static schedule) or one solve iteration (work stealing)
+    const long long nprod = (steal ? 1LL : (long long)n_outer) * (2LL * nfwd + 4LL * nadj);
     const int split = p.tc_split;
+    StealSched ss{p.sched, p.sched + 1, p.tiles, p.iters, reinterpret_cast<int*>(phnn_smem + 768)};
 
     if (warp < 8) {
         // ===== element threads =====
@@ -680,8 +735,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         c.qdone = 0;
         c.split = split;
         c.store = (c.hf == 0);
-        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, 128, TcCtx<SH>::WS_EXTRA);
-        c.stash = p.ws ? p.ws + (size_t)blockIdx.x * tile_floats + ws_floats_per_tile(NS, p.T, p.S, 128, 0) : nullptr;
+        c.stash = nullptr;
         mbar_wait(&bars[SH::B_SMALL], 0);
 #ifdef PHNN_TC_PROFILE
         for (int i = 0; i < 16; ++i) c.prof[i] = 0;
@@ -690,7 +744,12 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         c.aphase = 0;
         c.tlast = clock64();
 #endif
-        run_job(c, p, (long long)blockIdx.x, c.row, n_outer);
+        if (steal) {
+            run_job(c, p, ss, c.row);
+        } else {
+            StaticSched sched{(long long)blockIdx.x, n_outer, 0};
+            run_job(c, p, sched, c.row);
+        }
         tc_fence_before();
 #ifdef PHNN_TC_PROFILE
         if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 255) && p.dbg)
@@ -702,70 +761,84 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
 #endif
     } else if (warp == 8) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t a_base = smem_u32(phnn_smem + SH::OFF_A), b_base = smem_u32(phnn_smem + SH::OFF_B);
-            uint32_t ablk = 0, bent = 0;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_base = smem_u32(phnn_smem + SH::OFF_A), b_base = smem_u32(phnn_smem + SH::OFF_B);
+        uint32_t ablk = 0, bent = 0;
+        long long qtot = 0;  // products issued so far (accumulator / operand parity continues across units)
+        for (;;) {
+            if (steal && ss.grab() < 0) break;
+            if (lane == 0) {
 #pragma unroll 1
-            for (long long q = 0; q < nprod; ++q) {
-                const uint32_t acc = tbase + (uint32_t)(q & 1) * HID;
+                for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
+                    const uint32_t acc = tbase + (uint32_t)(qtot & 1) * HID;
 #pragma unroll 1
-                for (int kb = 0; kb < SH::NKB; ++kb) {
-                    const uint32_t slot = ablk & 1u;
-                    mbar_wait_sleep(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u, 32);
-                    const uint32_t a_hi = a_base + (slot * 2) * SH::A_TILE, a_lo = a_hi + SH::A_TILE;
-                    uint32_t e = bent % SH::NBE;
-                    mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, 32);
-                    tc_fence_after();
-                    uint32_t b_t = b_base + e * SH::B_TILE;
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, (kb | ks) ? 1u : 0u);
-                    if (split == 3) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_tf32(acc, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
-                    }
-                    umma_commit(&bars[SH::B_BEMPTY + e]);
-                    ++bent;
-                    if (split == 3) {
-                        e = bent % SH::NBE;
+                    for (int kb = 0; kb < SH::NKB; ++kb) {
+                        const uint32_t slot = ablk & 1u;
+                        mbar_wait_sleep(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u, 32);
+                        const uint32_t a_hi = a_base + (slot * 2) * SH::A_TILE, a_lo = a_hi + SH::A_TILE;
+                        uint32_t e = bent % SH::NBE;
                         mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, 32);
                         tc_fence_after();
-                        b_t = b_base + e * SH::B_TILE;
+                        uint32_t b_t = b_base + e * SH::B_TILE;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
+                            umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, (kb | ks) ? 1u : 0u);
+                        if (split == 3) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_tf32(acc, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
+                        }
                         umma_commit(&bars[SH::B_BEMPTY + e]);
                         ++bent;
+                        if (split == 3) {
+                            e = bent % SH::NBE;
+                            mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, 32);
+                            tc_fence_after();
+                            b_t = b_base + e * SH::B_TILE;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
+                            umma_commit(&bars[SH::B_BEMPTY + e]);
+                            ++bent;
+                        }
+                        umma_commit(&bars[SH::B_AEMPTY + slot]);
+                        ++ablk;
                     }
-                    umma_commit(&bars[SH::B_AEMPTY + slot]);
-                    ++ablk;
+                    umma_commit(&bars[SH::B_ACC + (qtot & 1)]);
                 }
-                umma_commit(&bars[SH::B_ACC + (q & 1)]);
             }
+            __syncwarp();
+            if (!steal) break;
         }
     } else {
         // ===== weight producer (TMA bulk copies of pre-swizzled K-blocks) =====
         if (lane == 0) {
             mbar_expect_tx(&bars[SH::B_SMALL], SH::SMALL * 4);
             bulk_g2s(phnn_smem + SH::OFF_SMALL, p.wsmall_tc, SH::SMALL * 4, &bars[SH::B_SMALL]);
-            uint32_t bent = 0;
+        }
+        uint32_t bent = 0;
+        long long qtot = 0;
+        for (;;) {
+            if (steal && ss.grab() < 0) break;
+            if (lane == 0) {
 #pragma unroll 1
-            for (long long q = 0; q < nprod; ++q) {
-                const unsigned char* src = p.wtc + (size_t)(q & 1) * SH::NKB * 2 * SH::B_TILE;
+                for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
+                    const unsigned char* src = p.wtc + (size_t)(qtot & 1) * SH::NKB * 2 * SH::B_TILE;
 #pragma unroll 1
-                for (int kb = 0; kb < SH::NKB; ++kb) {
-                    for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
-                        const uint32_t e = bent % SH::NBE;
-                        mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, 128);
-                        mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
-                        bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)(kb * 2 + hl) * SH::B_TILE, SH::B_TILE,
-                                 &bars[SH::B_BFULL + e]);
-                        ++bent;
+                    for (int kb = 0; kb < SH::NKB; ++kb) {
+                        for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
+                            const uint32_t e = bent % SH::NBE;
+                            mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, 128);
+                            mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
+                            bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)(kb * 2 + hl) * SH::B_TILE, SH::B_TILE,
+                                     &bars[SH::B_BFULL + e]);
+                            ++bent;
+                        }
                     }
                 }
             }
+            __syncwarp();
+            if (!steal) break;
         }
     }
     __syncthreads();
