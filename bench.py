@@ -363,6 +363,36 @@ def main():
                     "frac_of_measured_bf16_tensor_peak": (achieved / peaks["bf16_tflops_sustained"]) if peaks else None,
                     "kernel": "phnn_kernel<MK,NS,HID> (one launch per step)", "kernel_ms": kernel_ms}
 
+    # ---- second half of BASELINE.json's metric: pHNN RK4 rollout steps/s (config 2), same run ----
+    rollout_metric = None
+    try:
+        from phnn_mpc_b200.batched import rollout as _rollout
+        sdp = load_fixture("pendulum")
+        pkp = PackedModel({k: torch.from_numpy(v) for k, v in sdp.items()}, "phnn", device=dev)
+        g = torch.Generator().manual_seed(1)
+        Bp, Tp = 4096, 100
+        xp = torch.stack([(torch.rand(Bp, generator=g) * 2 - 1) * np.pi, torch.rand(Bp, generator=g) * 2 - 1], 1).to(dev)
+        Up = (torch.rand(Bp, Tp, 1, generator=g) * 4 - 2).to(dev)
+        for _ in range(3):
+            _rollout(pkp, xp, Up, 0.05, "rk4")
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _rollout(pkp, xp, Up, 0.05, "rk4")
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        rms = float(np.median(ts))
+        rollout_metric = {"metric": "phnn_rk4_rollout_instance_steps_per_s", "value": Bp * Tp / (rms * 1e-3), "unit": "instance-steps/s",
+                          "ms": rms, "config": "BASELINE cfg2: pendulum pHNN (shipped weights, h=64, learned G), 4096 initial states x H=100, "
+                                               "RK4, dt 0.05, one launch (FP32-FMA kernel)",
+                          "algorithmic_tflops": Bp * Tp * 73360 / (rms * 1e-3) / 1e12}
+    except Exception as ex:  # the headline line must still be printed
+        rollout_metric = {"error": repr(ex)}
+
     cpu = None
     if not args.no_cpu_baseline:
         r = cpu_leg(args, wl, 1, 0, budget_s=15.0)
@@ -374,7 +404,7 @@ def main():
             "config": dict(config, kernel_path=("tcgen05-3xTF32" if tmode == 3 else "tcgen05-TF32") if uses_tc else "fp32-fma",
                            l2="256 MiB buffer written between timed steps (L2 flush); per-step working set "
                                       "(stage checkpoints) also exceeds L2", gather_ms=gather_ms),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout_metric,
             "step_ms": step_ms}
     print(json.dumps(line))
     if world > 1:
