@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -319,7 +320,8 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     P.tiles = tiles;
     P.sched = nullptr;
     long long grid = tiles;
-    if (P.mode == MODE_SOLVE && P.iters > 0 && P.ws) {
+    static const bool no_steal = getenv("PHNN_NO_STEAL") != nullptr;  // experiment switch
+    if (P.mode == MODE_SOLVE && P.iters > 0 && P.ws && !no_steal) {
         // work-stealing solve: persistent CTAs pull (tile, iteration) units; the scheduler words sit after the
         // per-tile regions of the workspace and are zeroed on the stream before the launch
         const size_t tile_floats = ws_floats_per_tile(SH::NS, P.T, P.S, SH::TM, 2 * SH::HID);
