@@ -122,6 +122,31 @@ int phnn_mpc_solve(const phnn_pack *pack, const phnn_cost_desc *cost_desc, const
                    double beta1, double beta2, double eps, int iters, int return_mode, void *workspace,
                    size_t workspace_bytes, void *stream);
 
+/* ---- batched closed loop on the device (the callers either side of the solve) -------------------- */
+
+/* Device buffers of B concurrent cart-pole episodes.                                              */
+typedef struct phnn_episode {
+    double *state;            /* [B,4] float64 plant state [x, theta, x_dot, theta_dot], in/out          */
+    double *traj;             /* [B,steps+1,4] or NULL                                                  */
+    float *controls;          /* [B,steps] or NULL                                                      */
+    int *done_step;           /* [B] -1 while running, else the number of steps run when the plant ended */
+    int *stable_start;        /* [B] -1 or the step at which the current in-tolerance streak began       */
+    float *stable_duration;   /* [B] seconds                                                            */
+    int *stability_achieved;  /* [B] 0/1                                                                */
+    int steps;                /* episode length                                                         */
+} phnn_episode;
+
+/* One plant step for every running episode: stability bookkeeping of run_mpc_control
+ * (scripts/run_cartpole_mpc.py:138-159) on the current state, then CartPoleSimulator.step
+ * (src/cartpole_simulator.py:63-112) with force u[b*u_stride]; target/tol are HOST [4].             */
+int phnn_plant_step(const phnn_episode *ep, const float *u, long u_stride, int step, double dt, const double *target,
+                    const double *tol, double min_duration, long B, void *stream);
+/* x0 = float32(state) as the controllers cast it (src/mpc_controller.py:160-161); if traj is non-NULL
+ * also records state as traj[:,0,:].                                                               */
+int phnn_state_to_f32(const double *state, float *x0, double *traj, int steps, long B, void *stream);
+/* warm start: out[b,:] = [U[b,1:], 0] (src/mpc_controller_canonical.py:252-255); out != U.          */
+int phnn_shift_controls(const float *U, float *out, long B, int H, void *stream);
+
 /* Measurement utility (not part of the replaced path): launches a pure FFMA kernel of `blocks`
  * x 256 threads and returns the FLOPs it executes in *flops; bench.py times it with CUDA events
  * to get this GPU's sustained FP32-FMA rate, the roofline denominator of the FP32 path.        */

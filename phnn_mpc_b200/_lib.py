@@ -30,6 +30,12 @@ class CostDesc(ctypes.Structure):
                 ("barrier_weight", ctypes.c_float)]
 
 
+class Episode(ctypes.Structure):
+    _fields_ = [("state", ctypes.c_void_p), ("traj", ctypes.c_void_p), ("controls", ctypes.c_void_p),
+                ("done_step", ctypes.c_void_p), ("stable_start", ctypes.c_void_p), ("stable_duration", ctypes.c_void_p),
+                ("stability_achieved", ctypes.c_void_p), ("steps", ctypes.c_int)]
+
+
 _lib = None
 
 
@@ -62,6 +68,13 @@ def lib():
     L.phnn_pack_set_option.restype = ci
     L.phnn_pack_get_option.argtypes = [vp, ctypes.c_char_p]
     L.phnn_pack_get_option.restype = ll
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.phnn_plant_step.argtypes = [ctypes.POINTER(Episode), vp, ll, ci, cd, dp, dp, cd, ll, vp]
+    L.phnn_plant_step.restype = ci
+    L.phnn_state_to_f32.argtypes = [vp, vp, vp, ci, ll, vp]
+    L.phnn_state_to_f32.restype = ci
+    L.phnn_shift_controls.argtypes = [vp, vp, ll, ci, vp]
+    L.phnn_shift_controls.restype = ci
     L.phnn_ffma_probe.argtypes = [vp, ci, ci, vp, ctypes.POINTER(cd)]
     L.phnn_ffma_probe.restype = ci
     L.phnn_tf32_probe.argtypes = [vp, ci, ci, vp, ctypes.POINTER(cd)]
@@ -75,7 +88,7 @@ def lib():
 
 EXPORTS = ["phnn_last_error", "phnn_version", "phnn_pack_create", "phnn_pack_destroy", "phnn_pack_dims",
            "phnn_forward", "phnn_vjp", "phnn_rollout", "phnn_workspace_bytes", "phnn_cost_grad", "phnn_mpc_solve", "phnn_ffma_probe", "phnn_tf32_probe",
-           "phnn_pack_set_option", "phnn_pack_get_option"]
+           "phnn_pack_set_option", "phnn_pack_get_option", "phnn_plant_step", "phnn_state_to_f32", "phnn_shift_controls"]
 
 
 def check(rc, what):

@@ -554,3 +554,111 @@ extern "C" int phnn_tf32_probe(float* d_out, int n_mma, int blocks, void* stream
     if (flops) *flops = 2.0 * 128.0 * 256.0 * 8.0 * (double)n_mma * (double)blocks;
     return 0;
 }
+
+// =========================================================================================
+// Batched closed loop on the device: the plant step, the bookkeeping
+// of the reference's driver loop and the warm-start shift, so thousands of closed-loop episodes
+// advance without a host round trip per step.
+// =========================================================================================
+struct PlantArgs {
+    phnn_episode ep;
+    const float* u;
+    long long u_stride;
+    int step;
+    double dt, min_duration;
+    double target[4], tol[4];
+    long long B;
+};
+
+// CartPoleSimulator.step (src/cartpole_simulator.py:63-112, float64, explicit Euler, termination
+// |x| > 10 or |theta| > 0.5) preceded by the stability bookkeeping of run_mpc_control
+// (scripts/run_cartpole_mpc.py:138-159), one thread per plant.
+__global__ void plant_step_kernel(const PlantArgs a) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    double* s = a.ep.state + 4 * b;
+    double x = s[0], th = s[1], xd = s[2], thd = s[3];
+    const bool running = a.ep.done_step[b] < 0;
+    const float uf = running ? a.u[b * a.u_stride] : 0.f;
+    if (a.ep.controls) a.ep.controls[b * a.ep.steps + a.step] = uf;
+    if (running) {
+        // stability bookkeeping on the state the controller just saw
+        const double st[4] = {x, th, xd, thd};
+        bool within = true;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) within = within && (fabs(st[i] - a.target[i]) <= a.tol[i]);
+        if (within) {
+            if (a.ep.stable_start[b] < 0) a.ep.stable_start[b] = a.step;
+            const double dur = (double)(a.step - a.ep.stable_start[b] + 1) * a.dt;
+            a.ep.stable_duration[b] = (float)dur;
+            if (dur >= a.min_duration) a.ep.stability_achieved[b] = 1;
+        } else {
+            a.ep.stable_start[b] = -1;
+            a.ep.stable_duration[b] = 0.f;
+        }
+        const double gravity = 9.8, masscart = 1.0, masspole = 0.1, length = 0.5;
+        const double polemass_length = masspole * length, total_mass = masspole + masscart;
+        const double force = (double)uf;
+        const double c = cos(th), sn = sin(th);
+        const double temp = (force + polemass_length * thd * thd * sn) / total_mass;
+        const double thacc = (gravity * sn - c * temp) / (length * (4.0 / 3.0 - masspole * c * c / total_mass));
+        const double xacc = temp - polemass_length * thacc * c / total_mass;
+        x = x + a.dt * xd;
+        th = th + a.dt * thd;
+        xd = xd + a.dt * xacc;
+        thd = thd + a.dt * thacc;
+        s[0] = x; s[1] = th; s[2] = xd; s[3] = thd;
+        if (fabs(x) > 10.0 || fabs(th) > 0.5) a.ep.done_step[b] = a.step + 1;
+    }
+    if (a.ep.traj) {
+        double* t = a.ep.traj + ((size_t)b * (a.ep.steps + 1) + a.step + 1) * 4;
+        t[0] = x; t[1] = th; t[2] = xd; t[3] = thd;
+    }
+}
+
+extern "C" int phnn_plant_step(const phnn_episode* ep, const float* u, long u_stride, int step, double dt,
+                               const double* target, const double* tol, double min_duration, long B, void* stream) {
+    if (!ep || !ep->state || !ep->done_step || !ep->stable_start || !ep->stable_duration || !ep->stability_achieved || !u ||
+        !target || !tol || B < 0 || step < 0 || step >= ep->steps)
+        return fail(PHNN_E_ARG, "phnn_plant_step: bad argument");
+    if (B == 0) return 0;
+    PlantArgs a;
+    a.ep = *ep; a.u = u; a.u_stride = u_stride; a.step = step; a.dt = dt; a.min_duration = min_duration; a.B = B;
+    for (int i = 0; i < 4; ++i) { a.target[i] = target[i]; a.tol[i] = tol[i]; }
+    plant_step_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// x0[b,:] = float32(state[b,:]) -- the cast the controllers apply to the simulator's float64 state
+// (src/mpc_controller.py:160-161, src/mpc_controller_canonical.py:249); also writes traj[:,0,:] when step 0
+__global__ void state_to_f32_kernel(const double* __restrict__ state, float* __restrict__ x0, double* traj0, int traj_stride,
+                                    long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x0[i] = (float)state[i];
+    if (traj0) traj0[(i / 4) * (size_t)traj_stride + (i % 4)] = state[i];
+}
+extern "C" int phnn_state_to_f32(const double* state, float* x0, double* traj, int steps, long B, void* stream) {
+    if (!state || !x0 || B < 0) return fail(PHNN_E_ARG, "phnn_state_to_f32: bad argument");
+    if (B == 0) return 0;
+    state_to_f32_kernel<<<(unsigned)((B * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(state, x0, traj, (steps + 1) * 4, B * 4);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// warm start of MPCControllerCanonical.control: previous plan shifted left by one, zero appended
+// (src/mpc_controller_canonical.py:252-255)
+__global__ void shift_controls_kernel(const float* __restrict__ U, float* __restrict__ out, int H, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = (int)(i % H);
+    out[i] = (t + 1 < H) ? U[i + 1] : 0.f;
+}
+extern "C" int phnn_shift_controls(const float* U, float* out, long B, int H, void* stream) {
+    if (!U || !out || U == out || B < 0 || H <= 0) return fail(PHNN_E_ARG, "phnn_shift_controls: bad argument (in-place not allowed)");
+    if (B == 0) return 0;
+    shift_controls_kernel<<<(unsigned)((B * H + 255) / 256), 256, 0, (cudaStream_t)stream>>>(U, out, H, (long long)B * H);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}

@@ -266,8 +266,90 @@ def gen_canonical():
     print("canonical done; dx[0] =", out["rand_dx"][0])
 
 
+
+
+def gen_closed_loop():
+    """Closed loop of the reference pieces: CartPoleSimulator <-> controller, the
+    loop body of scripts/run_cartpole_mpc.py:121-176 and scripts/run_mpc_canonical.py:55-95 (warm start)."""
+    from cartpole_simulator import CartPoleSimulator  # reference
+    steps = 6
+    out = {}
+    # --- pHNN + MPCController, cold start every step (config 1) ---
+    torch.manual_seed(0)
+    model = pHNN(os.path.join(CFG, "cartpole_phnn.yaml"))
+    model.eval()
+    cfg = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    mpc = cfg["mpc"]
+    ctrl = MPCController(model, mpc["horizon"], cfg["cartpole"]["dt"], mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"],
+                         mpc["u_min"], mpc["u_max"], optimizer_type="Adam", lr=mpc["learning_rate"],
+                         max_iterations=mpc["optimizer_steps"])
+    x0s = np.array([[0.0, 0.1, 0.0, 0.0], [0.3, -0.12, 0.2, -0.4], [0.05, 0.02, -0.04, 0.03]])
+    tol = np.array(cfg["stability"]["tolerance"])
+    traj, ctr, hs, stable = [], [], [], []
+    for x0 in x0s:
+        sim = CartPoleSimulator(cfg["cartpole"]["dt"])
+        sim.reset(x0)
+        state = x0.copy()
+        states, controls, hams, within = [state.copy()], [], [], []
+        for _ in range(steps):
+            u = ctrl.compute_control(state)
+            controls.append(float(u[0]))
+            st = torch.tensor(state, dtype=torch.float32, requires_grad=True).unsqueeze(0)
+            _, H = ctrl.model(st, torch.tensor([[float(u[0])]], dtype=torch.float32))
+            hams.append(H.detach().item())
+            within.append(bool(np.all(np.abs(state - np.array(mpc["x_target"])) <= tol)))
+            state, done = sim.step(u)
+            states.append(state.copy())
+        traj.append(np.array(states)); ctr.append(np.array(controls)); hs.append(np.array(hams)); stable.append(np.array(within))
+    out.update({"sd/" + k: v.detach().numpy().copy() for k, v in model.state_dict().items()})
+    out.update(cl_x0=x0s, cl_traj=np.stack(traj), cl_u=np.stack(ctr).astype(np.float32), cl_H=np.stack(hs).astype(np.float32),
+               cl_within=np.stack(stable))
+    # plant alone: 50 steps under a fixed control pattern, float64
+    sim = CartPoleSimulator(0.02)
+    sim.reset(np.array([0.1, 0.2, -0.3, 0.4]))
+    ps = [sim.get_state()]
+    us = (np.sin(np.arange(50) * 0.7) * 12.0).astype(np.float32)
+    dones = []
+    for u in us:
+        s, d = sim.step(np.array([u], np.float32))
+        ps.append(s); dones.append(d)
+    out.update(plant_traj=np.array(ps), plant_u=us, plant_done=np.array(dones))
+    np.savez(os.path.join(HERE, "closed_loop.npz"), **out)
+    # --- canonical + MPCControllerCanonical, warm start from the shifted previous plan ---
+    torch.manual_seed(0)
+    cm = pHNN_Canonical(os.path.join(CFG, "cartpole_phnn.yaml"))
+    cm.eval()
+    pcfg = yaml.safe_load(open(os.path.join(CFG, "pole_stabilization.yaml")))
+    cc = create_mpc_controller(cm, pcfg)
+    x0c = np.array([[0.0, 0.05, 0.0, 0.0], [0.2, -0.08, 0.1, 0.2]])
+    ctraj, cctr = [], []
+    for x0 in x0c:
+        sim = CartPoleSimulator(pcfg["cartpole"]["dt"])
+        sim.reset(x0)
+        state, u_prev = x0.copy(), None
+        states, controls = [state.copy()], []
+        for _ in range(steps):
+            u, info = cc.control(state, u_prev)
+            u_prev = info["u_sequence"]
+            controls.append(float(u[0]))
+            state, done = sim.step(u)
+            states.append(state.copy())
+        ctraj.append(np.array(states)); cctr.append(np.array(controls))
+    outc = {"sd/" + k: v.detach().numpy().copy() for k, v in cm.state_dict().items()}
+    outc.update(cl_x0=x0c, cl_traj=np.stack(ctraj), cl_u=np.stack(cctr).astype(np.float32))
+    np.savez(os.path.join(HERE, "closed_loop_canonical.npz"), **outc)
+    print("closed loop done; u[0] =", out["cl_u"][0], "canon u[0] =", outc["cl_u"][0])
+
+
 if __name__ == "__main__":
-    gen_pendulum()
-    gen_cartpole(128, 0, "cartpole_h128")
-    gen_cartpole(256, 1234, "cartpole_h256")
-    gen_canonical()
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop"]
+    if "pendulum" in which:
+        gen_pendulum()
+    if "h128" in which:
+        gen_cartpole(128, 0, "cartpole_h128")
+    if "h256" in which:
+        gen_cartpole(256, 1234, "cartpole_h256")
+    if "canonical" in which:
+        gen_canonical()
+    if "closed_loop" in which:
+        gen_closed_loop()
