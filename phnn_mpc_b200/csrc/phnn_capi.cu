@@ -4,6 +4,7 @@
 #include "../../include/phnn_mpc.h"
 #include "phnn_kernel.cuh"
 #include "phnn_tc_kernel.cuh"
+#include "phnn_lat_kernel.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -19,6 +20,7 @@ struct phnn_pack {
     int device, num_sms;
     int tc_mode;          // 0: FP32-FMA kernel only; 3: tcgen05 3xTF32 when eligible; 1: tcgen05 plain TF32
     long tc_min_batch;    // smallest B routed to the tcgen05 kernel
+    long lat_max_batch;   // largest B routed to the one-CTA-per-instance latency kernel (0 = never)
     float* d_small;
     float* d_big;
     unsigned char* d_wtc;
@@ -70,6 +72,24 @@ static bool has_tc_shape(int mk, int n, int h) {
 #define X(MK, NS, HID) \
     if (mk == MK && n == NS && h == HID) return true;
     PHNN_TC_SHAPES(X)
+#undef X
+    return false;
+}
+
+// shapes with a latency-kernel instantiation (W2 and W2^T must fit in shared memory: h <= 128)
+#define PHNN_LAT_SHAPES(X) \
+    X(MK_PHNN, 4, 64)      \
+    X(MK_PHNN, 4, 128)     \
+    X(MK_PHNN, 2, 64)      \
+    X(MK_PHNN_GNET, 2, 64) \
+    X(MK_PHNN_GNET, 4, 128) \
+    X(MK_CANON, 4, 64)     \
+    X(MK_CANON, 4, 128)
+
+static bool has_lat_shape(int mk, int n, int h) {
+#define X(MK, NS, HID) \
+    if (mk == MK && n == NS && h == HID) return true;
+    PHNN_LAT_SHAPES(X)
 #undef X
     return false;
 }
@@ -221,6 +241,7 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         return cuda_fail(e, "phnn_pack_create");
     }
     pk->small_floats = small.size();
+    pk->lat_max_batch = has_lat_shape(mk, n, h) ? 2L * pk->num_sms : 0;
     KParams& P = pk->base;
     P.wsmall = pk->d_small;
     P.wbig = pk->d_big;
@@ -269,6 +290,11 @@ extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) 
         pk->tc_min_batch = value;
         return 0;
     }
+    if (!strcmp(key, "latency_max_batch")) {
+        if (value > 0 && !has_lat_shape(pk->mk, pk->n, pk->h)) return fail(PHNN_E_UNSUPPORTED, "no latency kernel for this model shape");
+        pk->lat_max_batch = value;
+        return 0;
+    }
     return fail(PHNN_E_ARG, "unknown option %s", key);
 }
 
@@ -280,6 +306,7 @@ extern "C" long phnn_pack_get_option(const phnn_pack* pk, const char* key) {
     if (!pk || !key) return -1;
     if (!strcmp(key, "tensor_mode")) return pk->tc_mode;
     if (!strcmp(key, "tensor_min_batch")) return pk->tc_min_batch;
+    if (!strcmp(key, "latency_max_batch")) return pk->lat_max_batch;
     return -1;
 }
 
@@ -306,6 +333,17 @@ static int launch_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
     const int threads = ((int)ng * SH::NWG + 1) * 32;
     kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <class SH>
+static int launch_lat_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
+    auto kern = phnn_lat_kernel<SH::MK, SH::NS, SH::HID>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
+    P.ng = 1;
+    kern<<<(unsigned)P.B, SH::HID, SH::SMEM_BYTES, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    (void)pk;
     return 0;
 }
 
@@ -340,6 +378,15 @@ static int launch(const phnn_pack* pk, KParams& P, void* stream) {
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != pk->device) CUDA_TRY(cudaSetDevice(pk->device));
     int rc = fail(PHNN_E_UNSUPPORTED, "no kernel instantiation");
+    // small batches: one CTA per instance (latency path)
+    if (pk->lat_max_batch > 0 && P.B <= pk->lat_max_batch && has_lat_shape(pk->mk, pk->n, pk->h)) {
+#define X(MK, NS, HID) \
+    if (pk->mk == MK && pk->n == NS && pk->h == HID) rc = launch_lat_shape<LatShape<MK, NS, HID>>(pk, P, (cudaStream_t)stream);
+        PHNN_LAT_SHAPES(X)
+#undef X
+        if (prev != pk->device) cudaSetDevice(prev);
+        return rc;
+    }
     // tcgen05 path only when batch x hidden width make the layer products a real dense contraction
     // (phnn_vjp carries no workspace for the tcgen05 kernel's activation stash: it stays on the FP32 kernel)
     if (pk->tc_mode != 0 && pk->d_wtc && P.B >= pk->tc_min_batch && P.mode != MODE_VJP) {

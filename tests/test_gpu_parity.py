@@ -31,7 +31,10 @@ def env():
     def get(name):
         if name not in packs:
             z, sd = load_golden(name)
-            packs[name] = (z, sd, PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, KINDS[name]))
+            pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, KINDS[name])
+            if pk.get_option("latency_max_batch") > 0:
+                pk.set_option("latency_max_batch", 0)      # these tests exercise the batched FP32-FMA kernel
+            packs[name] = (z, sd, pk)
         return packs[name]
 
     return ops, get
@@ -320,3 +323,93 @@ def test_tc_matches_fp32_kernel_and_oracle_cfg4_shape(tc_env, env):
         assert np.abs(U.cpu().numpy() - Uo).max() < 0.02 * 0.015 + 1e-5
         outs.append(U.cpu().numpy())
     assert np.abs(outs[0] - outs[1]).max() < 0.02 * 0.015 + 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# latency kernel (one CTA per instance; the default route for B <= 2 x SM count, hidden <= 128)
+# ---------------------------------------------------------------------------------------------
+LAT_MODELS = ["pendulum", "cartpole_h128", "canonical"]
+
+
+@pytest.fixture(scope="module")
+def lat_env(env):
+    from phnn_mpc_b200.packing import PackedModel
+    ops, _ = env
+    packs = {}
+
+    def get_lat(name):
+        if name not in packs:
+            z, sd = load_golden(name)
+            pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, KINDS[name])
+            assert pk.get_option("latency_max_batch") >= 32
+            packs[name] = (z, sd, pk)
+        return packs[name]
+
+    return ops, get_lat
+
+
+@pytest.mark.parametrize("name", LAT_MODELS)
+def test_lat_forward_vjp_golden(lat_env, name):
+    ops, get_lat = lat_env
+    z, sd, pk = get_lat(name)
+    dx, H = ops.forward(pk.handle, cu(z["rand_x"]), cu(z["rand_u"]))
+    assert rel_err(dx.cpu().numpy(), z["rand_dx"]) < STEP_TOL
+    assert rel_err(H.cpu().numpy(), z["rand_H"]) < STEP_TOL
+    xb, ub = ops.vjp(pk.handle, cu(z["rand_x"]), cu(z["rand_u"]), cu(z["rand_v"]))
+    assert rel_err(xb.cpu().numpy(), z["rand_gx"]) < STEP_TOL
+    assert rel_err(ub.cpu().numpy(), z["rand_gu"]) < STEP_TOL
+    # a single instance (the reference's own call shape)
+    dx1, H1 = ops.forward(pk.handle, cu(z["rand_x"][:1]), cu(z["rand_u"][:1]))
+    assert rel_err(dx1.cpu().numpy(), z["rand_dx"][:1]) < STEP_TOL
+
+
+def test_lat_pendulum_rollouts(lat_env):
+    ops, get_lat = lat_env
+    z, sd, pk = get_lat("pendulum")
+    U10 = np.repeat(z["anchor_u"][:, None, :], 10, 1)
+    for integ, iid in (("rk4", 1), ("euler", 0)):
+        for emode, key in ((1, "anchor_%s_" + integ), (2, "anchor_%s2_" + integ)):
+            tr, en = ops.rollout(pk.handle, cu(z["anchor_x"]), cu(U10), 0.05, iid, emode)
+            assert rel_err(tr.cpu().numpy(), z[key % "traj"]) < HORIZON_TOL
+            assert rel_err(en.cpu().numpy(), z[key % "en"]) < HORIZON_TOL
+    tr, _ = ops.rollout(pk.handle, cu(z["cfg2_x0"]), cu(z["cfg2_U"]), 0.05, 1, 0)
+    assert rel_err(tr.cpu().numpy(), z["cfg2_traj_rk4"]) < 2e-4
+
+
+@pytest.mark.parametrize("name", LAT_MODELS)
+@pytest.mark.parametrize("integ", ["euler", "rk4"])
+def test_lat_cost_grad_and_solve_golden(lat_env, name, integ):
+    ops, get_lat = lat_env
+    z, sd, pk = get_lat(name)
+    iid = {"euler": 0, "rk4": 1}[integ]
+    dt, lr = float(z["mpc_dt"]), float(z["mpc_lr"])
+    ca = cost_args(z)
+    p = "mpc_%s_" % integ
+    cost, g, tr = ops.cost_grad(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, True, True)
+    assert rel_err(cost.cpu().numpy(), z[p + "hist"][0]) < HORIZON_TOL
+    assert rel_err(g.cpu().numpy(), z[p + "grad0"]) < HORIZON_TOL
+    lo, hi = [float(v) for v in z["mpc_bounds"]]
+    out = (z["mpc_U0"] < lo) | (z["mpc_U0"] > hi)
+    assert np.all(g.cpu().numpy()[out] == 0)
+    iters = z[p + "hist"].shape[0]
+    for mode, key in ((0, "U_last"), (1, "U_best")):
+        U, hist, best = ops.mpc_solve(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, lr, 0.9, 0.999, 1e-8,
+                                      iters, mode, True)
+        assert rel_err(hist.cpu().numpy(), z[p + "hist"]) < HORIZON_TOL
+        assert np.abs(U.cpu().numpy() - z[p + key]).max() < 0.02 * lr + 1e-5
+        assert rel_err(best.cpu().numpy(), z[p + "best"]) < HORIZON_TOL
+
+
+def test_lat_matches_batched_kernel(lat_env, env):
+    """same inputs through the latency kernel and the batched FP32 kernel"""
+    ops, get_lat = lat_env
+    _, get = env
+    for name in LAT_MODELS:
+        z, sd, pk_lat = get_lat(name)
+        _, _, pk_fp = get(name)
+        ca = cost_args(z)
+        dt, lr = float(z["mpc_dt"]), float(z["mpc_lr"])
+        outs = [ops.mpc_solve(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, 1, *ca, lr, 0.9, 0.999, 1e-8, 4, 0, True)
+                for pk in (pk_lat, pk_fp)]
+        assert rel_err(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy()) < HORIZON_TOL
+        assert np.abs(outs[0][0].cpu().numpy() - outs[1][0].cpu().numpy()).max() < 0.02 * lr + 1e-5
