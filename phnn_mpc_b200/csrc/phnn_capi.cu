@@ -229,7 +229,7 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         if (e == cudaSuccess) e = cudaMemcpy(pk->d_wtc, wtc.data(), wtc.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pk->d_small_tc, stc.data(), stc.size() * sizeof(float), cudaMemcpyHostToDevice);
         pk->tc_mode = 3;
-        pk->tc_min_batch = 4096;
+        pk->tc_min_batch = 1;  // measured: the tcgen05 kernel beats the FP32-FMA kernel at every batch size (tools/gpu_crossover.py)
     }
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
@@ -241,7 +241,9 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         return cuda_fail(e, "phnn_pack_create");
     }
     pk->small_floats = small.size();
-    pk->lat_max_batch = has_lat_shape(mk, n, h) ? 2L * pk->num_sms : 0;
+    // crossover measured on B200 (tools/gpu_crossover.py): the latency kernel wins up to ~64 instances per SM at
+    // h = 64, ~14 per SM at h = 128 against the FP32-FMA kernel and ~6 per SM against the tcgen05 kernel
+    pk->lat_max_batch = !has_lat_shape(mk, n, h) ? 0 : (h <= 64 ? 64L : (pk->d_wtc ? 6L : 14L)) * pk->num_sms;
     KParams& P = pk->base;
     P.wsmall = pk->d_small;
     P.wbig = pk->d_big;

@@ -34,6 +34,8 @@ def env():
             pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, KINDS[name])
             if pk.get_option("latency_max_batch") > 0:
                 pk.set_option("latency_max_batch", 0)      # these tests exercise the batched FP32-FMA kernel
+            if pk.get_option("tensor_mode") > 0:
+                pk.set_option("tensor_mode", 0)
             packs[name] = (z, sd, pk)
         return packs[name]
 
@@ -238,6 +240,7 @@ def tc_env(env):
             z, sd = load_golden(name)
             pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, "phnn")
             pk.set_option("tensor_min_batch", 0)
+            pk.set_option("latency_max_batch", 0)
             pk.set_option("tensor_mode", mode)
             assert pk.get_option("tensor_mode") == mode
             packs[key] = (z, sd, pk)
