@@ -98,6 +98,15 @@ class PackedModel:
         self.handle = handle.value
         self._fin = weakref.finalize(self, L.phnn_pack_destroy, ctypes.c_void_p(self.handle))
 
+    @classmethod
+    def from_file(cls, path, device=None):
+        """device image straight from a PHNNPK01 file or a reference ``.pth`` checkpoint (weights_io.py)"""
+        from . import weights_io
+        with open(path, "rb") as f:
+            packed = f.read(8) == weights_io.MAGIC
+        sd = weights_io.load_packed(path)[0] if packed else weights_io.load_reference_checkpoint(path)
+        return cls({k: torch.from_numpy(v) for k, v in sd.items()}, device=device)
+
     def set_option(self, key, value):
         """kernel selection knobs: 'tensor_mode' (0 FP32-FMA, 3 tcgen05 3xTF32, 1 tcgen05 TF32), 'tensor_min_batch'"""
         _lib.check(_lib.lib().phnn_pack_set_option(ctypes.c_void_p(self.handle), key.encode(), int(value)),

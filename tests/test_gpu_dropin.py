@@ -159,3 +159,14 @@ def test_closed_loop_with_plant_short():
         xa = tmp - 0.05 * tha * np.cos(th) / 1.1
         state = np.array([x + 0.02 * xd, th + 0.02 * thd, xd + 0.02 * xa, thd + 0.02 * tha])
     assert np.isfinite(state).all()
+
+
+def test_pack_from_packed_file(tmp_path):
+    """device image straight from a PHNNPK01 file gives the same forward as the state_dict route"""
+    from phnn_mpc_b200 import ops, weights_io
+    from phnn_mpc_b200.packing import PackedModel
+    z, sd = load_golden("canonical")
+    f = weights_io.save_packed(str(tmp_path / "c.phnnpk"), sd)
+    pk = PackedModel.from_file(f)
+    dx, H = ops.forward(pk.handle, torch.from_numpy(z["rand_x"]).cuda(), torch.from_numpy(z["rand_u"]).cuda())
+    assert rel_err(dx.cpu().numpy(), z["rand_dx"]) < 1e-5 and rel_err(H.cpu().numpy(), z["rand_H"]) < 1e-5

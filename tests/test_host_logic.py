@@ -159,3 +159,30 @@ def test_sharded_solve_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("OK") == 2
+
+
+def test_packed_weight_file_roundtrip_and_reference_checkpoint_layouts(tmp_path):
+    """PHNNPK01 file <-> state_dict, and both .pth layouts the reference's drivers accept."""
+    from phnn_mpc_b200 import weights_io
+    from phnn_mpc_b200.dropin.pHNN import pHNN
+    for name in ("pendulum", "cartpole_h128", "canonical"):
+        _, sd = load_golden(name)
+        f = weights_io.save_packed(str(tmp_path / (name + ".phnnpk")), sd)
+        back, meta = weights_io.load_packed(f)
+        assert sorted(back) == sorted(sd) and all(np.array_equal(back[k], sd[k]) for k in sd)
+        assert meta["kind"] == ("canonical" if name == "canonical" else "phnn")
+        assert meta["learned_G"] == (name == "pendulum") and meta["h"] == sd["H_net.net.0.weight"].shape[0]
+    _, sd = load_golden("cartpole_h128")
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    raw, wrapped = str(tmp_path / "raw.pth"), str(tmp_path / "wrapped.pth")
+    torch.save(tsd, raw)
+    torch.save({"model_state_dict": tsd, "epoch": 860}, wrapped)
+    for p in (raw, wrapped):
+        got = weights_io.load_reference_checkpoint(p)
+        assert all(np.array_equal(got[k], sd[k]) for k in sd)
+    m = pHNN(os.path.join(CONFIGS, "cartpole_phnn.yaml"))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_io.load_packed(
+        weights_io.save_packed(str(tmp_path / "x.phnnpk"), sd))[0].items()})
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.bin").write_bytes(b"notapack" + b"\0" * 64)
+        weights_io.load_packed(str(tmp_path / "bad.bin"))
