@@ -23,7 +23,7 @@ MAGIC = b"PHNNPK01"
 def _to_np(v):
     if hasattr(v, "detach"):
         v = v.detach().cpu().numpy()
-    return np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+    return np.asarray(v, dtype=np.float32, order="C")  # (ascontiguousarray would turn 0-d scalars into shape (1,))
 
 
 def load_reference_checkpoint(path):
