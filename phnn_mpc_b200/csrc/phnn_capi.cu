@@ -66,7 +66,9 @@ extern "C" int phnn_version(void) { return 100; }
 // shapes with a tcgen05 instantiation (cart-pole pHNN, fixed G)
 #define PHNN_TC_SHAPES(X) \
     X(MK_PHNN, 4, 128)    \
-    X(MK_PHNN, 4, 256)
+    X(MK_PHNN, 4, 256)    \
+    X(MK_CANON, 4, 128)   \
+    X(MK_CANON, 4, 256)
 
 static bool has_tc_shape(int mk, int n, int h) {
 #define X(MK, NS, HID) \
@@ -126,7 +128,8 @@ static void fill_tc_big(const phnn_model_desc* d, std::vector<unsigned char>& ou
 // output weights + 2 pad
 static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
     const int h = d->h, n = d->n;   // n == 4 for every tcgen05 shape
-    s.assign((size_t)h * (8 + 4 + 12), 0.f);
+    const bool has_r = d->kind == PHNN_KIND_PHNN;
+    s.assign((size_t)h * (has_r ? 8 + 4 + 12 : 8), 0.f);
     float* rA = s.data();
     float* rB = rA + (size_t)h * 8;
     float* rC = rB + (size_t)h * 4;
@@ -135,6 +138,7 @@ static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
         rA[k * 8 + 4] = d->b1[k];
         rA[k * 8 + 5] = d->b2[k];
         rA[k * 8 + 6] = d->W3[k];
+        if (!has_r) continue;
         rA[k * 8 + 7] = d->br1[k];
         for (int i = 0; i < n; ++i) rB[k * 4 + i] = d->Wr1[k * n + i];
         for (int a = 0; a < n; ++a)

@@ -17,6 +17,8 @@
 //     hi = cvt.rna.tf32(x); A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo, accumulated in FP32 in TMEM
 //     (measured 2e-6 relative on a K=256 product vs 6e-7 for an FP32 FMA chain and 3e-4 for
 //     plain TF32; tools/tc_probe.cu).  split = 1 selects plain TF32 (looser, stated tolerance).
+//   * kinds: pHNN with fixed G (R_net on the element threads, its output layer folded with the
+//     symmetrisation to 10 columns) and the canonical pHNN (mass-matrix transforms per thread).
 //   * thread = instance: element thread (row, half) owns 16 of every 32 hidden units of one
 //     instance (tcgen05.ld 32x32b gives a thread its own TMEM lane), so every reduction over
 //     the hidden dimension is a private register loop; the two halves of an instance meet in
@@ -30,8 +32,9 @@ namespace phnn {
 
 template <int MK_, int NS_, int HID_>
 struct TcShape {
-    static_assert(MK_ == MK_PHNN && NS_ == 4, "tensor-core path: cart-pole pHNN (fixed G, n = 4)");
+    static_assert((MK_ == MK_PHNN || MK_ == MK_CANON) && NS_ == 4, "tensor-core path: cart-pole pHNN (fixed G) and canonical pHNN, n = 4");
     static constexpr int MK = MK_, NS = NS_, HID = HID_, NN = NS * NS;
+    static constexpr bool HAS_R = (MK != MK_CANON);
     static constexpr int TM = 128;         // instances per tile (UMMA M)
     static constexpr int NKB = HID / 32;   // K-blocks of 32 tf32 (one 128-byte swizzle row)
     static constexpr int A_TILE = TM * 128;   // bytes of one A K-block (hi or lo)
@@ -43,8 +46,8 @@ struct TcShape {
     static constexpr int NSYM = 10, RC = 12;
     static constexpr int O_RA = 0;
     static constexpr int O_RB = O_RA + HID * 8;
-    static constexpr int O_RC = O_RB + HID * 4;
-    static constexpr int SMALL = O_RC + HID * RC;
+    static constexpr int O_RC = O_RB + (HAS_R ? HID * 4 : 0);
+    static constexpr int SMALL = O_RC + (HAS_R ? HID * RC : 0);
     static constexpr int XW = 12 + 1 + NS;    // floats per thread in the pair exchange (S partial, H, dH)
     // shared memory map (bytes)
     static constexpr int OFF_A = 1024;                        // 2 slots x (hi, lo)
@@ -293,7 +296,7 @@ __device__ __forceinline__ void tc_acc_S(const float* rC, int k, float r, float*
 // phase A of both evaluations: a1 = tanh(W1 y + b1) -> A ring (product z2 = W2 a1), and the
 // R_net hidden layer with its symmetrised output sums
 template <bool STASH, class SH>
-__device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&y)[4], float* Sp) {
+__device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], const float (&y)[4], float* Sp) {
     const float* rA = c.small() + SH::O_RA;
     const float* rB = c.small() + SH::O_RB;
     const float* rC = c.small() + SH::O_RC;
@@ -307,19 +310,28 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&y)[4], f
             for (int e = 0; e < 4; ++e) {
                 const int k = kb * 32 + c.hf * 16 + q * 4 + e;
                 const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
-                av[e] = tanh_tc(dot4(w1, y, m.x));
-                const float r = tanh_tc(dot4(lds4(rB + k * 4), y, m.w));
-#ifndef PHNN_EXP_SKIP_ACCS
-                tc_acc_S(rC, k, r, Sp);
-#else
-                Sp[0] += r;
-#endif
+                av[e] = tanh_tc(dot4(w1, z, m.x));
+                if constexpr (SH::HAS_R) {
+                    const float r = tanh_tc(dot4(lds4(rB + k * 4), y, m.w));
+                    tc_acc_S(rC, k, r, Sp);
+                }
             }
             if (STASH) *c.stash4(1, kb, q) = make_float4(av[0], av[1], av[2], av[3]);
             c.a_put4(slot, q, av);
             if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
         }
         c.a_end(slot);
+    }
+}
+
+// canonical model: rows 2,3 of (J - diag r) g + G u  (src/pHNN_canonical.py:227,247)
+__device__ __forceinline__ void tc_canon_pdot(const KParams& p, const float* g, float u, float (&pd)[2]) {
+#pragma unroll
+    for (int r = 2; r < 4; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = fmaf(p.Jm[r * 4 + k] - (r == k ? p.rdiag[r] : 0.f), g[k], s);
+        pd[r - 2] = s + p.Gv[r] * u;
     }
 }
 
@@ -338,7 +350,18 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
 #ifdef PHNN_TC_PROFILE
     c.aphase = 0;
 #endif
-    tc_phase_a1<false>(c, y, X);
+    float z[4];
+    Canon cq = {};
+    if constexpr (SH::MK == MK_CANON) {
+        cq = canon_of(p, y[1]);
+        z[0] = y[0]; z[1] = y[1];
+        z[2] = p.ma * y[2] + cq.beta * y[3];  // p = M(q) qdot
+        z[3] = cq.beta * y[2] + p.mc * y[3];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z[i] = y[i];
+    }
+    tc_phase_a1<false>(c, z, y, X);
 #ifdef PHNN_TC_PROFILE
     c.aphase = 1;
 #endif
@@ -379,7 +402,7 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
             for (int i = 0; i < 16; ++i) {
                 const int k = kb * 32 + c.hf * 16 + i;
                 const float4 w1 = lds4(rA + k * 8);
-                const float a1 = tanh_tc(dot4(w1, y, rA[k * 8 + 4]));
+                const float a1 = tanh_tc(dot4(w1, z, rA[k * 8 + 4]));
                 if ((i & 3) == 3) sched_fence();
                 const float d1 = fmaf(-a1, a1, 1.f) * __uint_as_float(gr[i]);
                 g0 = fmaf(w1.x, d1, g0); g1s = fmaf(w1.y, d1, g1s); g2 = fmaf(w1.z, d1, g2); g3 = fmaf(w1.w, d1, g3);
@@ -392,19 +415,28 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
     c.exchange(X);
     TCP_MARK(c, 5);
     Hval = X[12] + p.b3;
-    float S[4][4];
-    tc_make_S(p, X, S);
+    if constexpr (SH::MK == MK_CANON) {
+        float pd[2];
+        tc_canon_pdot(p, X + 13, u, pd);
+        f[0] = cq.n11 * z[2] + cq.n12 * z[3];  // qdot = M^-1 p
+        f[1] = cq.n12 * z[2] + cq.n22 * z[3];
+        f[2] = cq.n11 * pd[0] + cq.n12 * pd[1];  // qddot ~= M^-1 pdot
+        f[3] = cq.n12 * pd[0] + cq.n22 * pd[1];
+    } else {
+        float S[4][4];
+        tc_make_S(p, X, S);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        float s = 0.f;
+        for (int a = 0; a < 4; ++a) {
+            float s = 0.f;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            float Rab = 0.f;
+            for (int b = 0; b < 4; ++b) {
+                float Rab = 0.f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) Rab = fmaf(S[a][k], S[b][k], Rab);
-            s = fmaf(p.Jm[a * 4 + b] - Rab, X[13 + b], s);
+                for (int k = 0; k < 4; ++k) Rab = fmaf(S[a][k], S[b][k], Rab);
+                s = fmaf(p.Jm[a * 4 + b] - Rab, X[13 + b], s);
+            }
+            f[a] = s + p.Gv[a] * u;
         }
-        f[a] = s + p.Gv[a] * u;
     }
 }
 
@@ -427,24 +459,45 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
 #ifdef PHNN_TC_PROFILE
     c.aphase = 2;
 #endif
-    tc_phase_a1<true>(c, y, Sp);
-#ifdef PHNN_TC_PROFILE
-    c.aphase = 3;
-#endif
+    float z[4], w[4], S[4][4], sv[4];
+    Canon cq = {};
+    float pb[2] = {0.f, 0.f}, pdb[2] = {0.f, 0.f};
+    if constexpr (SH::MK == MK_CANON) {
+        cq = canon_of(p, y[1]);
+        z[0] = y[0]; z[1] = y[1];
+        z[2] = p.ma * y[2] + cq.beta * y[3];
+        z[3] = cq.beta * y[2] + p.mc * y[3];
+        pb[0] = cq.n11 * v[0] + cq.n12 * v[1];
+        pb[1] = cq.n12 * v[0] + cq.n22 * v[1];
+        pdb[0] = cq.n11 * v[2] + cq.n12 * v[3];
+        pdb[1] = cq.n12 * v[2] + cq.n22 * v[3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // w = (J - diag r)^T [0, 0, pdb]
+            float s = 0.f;
+#pragma unroll
+            for (int r = 2; r < 4; ++r) s = fmaf(p.Jm[r * 4 + k] - (r == k ? p.rdiag[r] : 0.f), pdb[r - 2], s);
+            w[k] = s;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z[i] = y[i];
+    }
+    tc_phase_a1<true>(c, z, y, Sp);
     TCP_MARK(c, 6);
-    c.exchange(Sp);
-    float S[4][4], sv[4], w[4];
-    tc_make_S(p, Sp, S);
+    if constexpr (SH::HAS_R) {
+        c.exchange(Sp);
+        tc_make_S(p, Sp, S);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) sv[a] = fmaf(S[a][3], v[3], fmaf(S[a][2], v[2], fmaf(S[a][1], v[1], S[a][0] * v[0])));
+        for (int a = 0; a < 4; ++a) sv[a] = fmaf(S[a][3], v[3], fmaf(S[a][2], v[2], fmaf(S[a][1], v[1], S[a][0] * v[0])));
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {  // w = (J - J^T)^T v - S (S v)
-        float s = 0.f;
+        for (int a = 0; a < 4; ++a) {  // w = (J - J^T)^T v - S (S v)
+            float s = 0.f;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s = fmaf(p.Jm[b * 4 + a], v[b], s);
+            for (int b = 0; b < 4; ++b) s = fmaf(p.Jm[b * 4 + a], v[b], s);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s = fmaf(-S[a][b], sv[b], s);
-        w[a] = s;
+            for (int b = 0; b < 4; ++b) s = fmaf(-S[a][b], sv[b], s);
+            w[a] = s;
+        }
     }
     // ---- B1: a2 (stashed), delta2 -> product 2 ----
     {
@@ -570,7 +623,7 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     float G4[4] = {Y[0], Y[1], Y[2], Y[3]};
     c.exchange(G4);
     float X4[4] = {Y[4], Y[5], Y[6], Y[7]};
-    {
+    if constexpr (SH::HAS_R) {
         // cotangent of S: -(v t^T + g s^T) symmetrised, packed with multiplicity 2 off the diagonal
         float tg[4], Rb[12];
 #pragma unroll
@@ -628,9 +681,30 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     TCP_MARK(c, 14);
     c.exchange(X4);
     TCP_MARK(c, 5);
+    if constexpr (SH::MK == MK_CANON) {
+        // chain through z = [q, M(theta) qdot] and M^-1(theta) (src/mass_matrix.py:310-362), SURVEY.md Appendix A
+        float pd[2];
+        tc_canon_pdot(p, G4, u, pd);
+        const float dbeta = -p.mb * cq.sth;
+        const float dD = -2.f * cq.beta * dbeta;
+        const float iD2 = 1.f / (cq.D * cq.D);
+        const float dn11 = -p.mc * iD2 * dD;
+        const float dn12 = -dbeta / cq.D + cq.beta * iD2 * dD;
+        const float dn22 = -p.ma * iD2 * dD;
+        float thbar = v[0] * (dn11 * z[2] + dn12 * z[3]) + v[1] * (dn12 * z[2] + dn22 * z[3]);
+        thbar += v[2] * (dn11 * pd[0] + dn12 * pd[1]) + v[3] * (dn12 * pd[0] + dn22 * pd[1]);
+        float zb[4] = {X4[0], X4[1], X4[2] + pb[0], X4[3] + pb[1]};
+        thbar += dbeta * (zb[2] * y[3] + zb[3] * y[2]);
+        xbar[0] = zb[0];
+        xbar[1] = zb[1] + thbar;
+        xbar[2] = p.ma * zb[2] + cq.beta * zb[3];
+        xbar[3] = cq.beta * zb[2] + p.mc * zb[3];
+        ubar = p.Gv[2] * pdb[0] + p.Gv[3] * pdb[1];
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) xbar[i] = X4[i];
-    ubar = fmaf(p.Gv[3], v[3], fmaf(p.Gv[2], v[2], fmaf(p.Gv[1], v[1], p.Gv[0] * v[0])));
+        for (int i = 0; i < 4; ++i) xbar[i] = X4[i];
+        ubar = fmaf(p.Gv[3], v[3], fmaf(p.Gv[2], v[2], fmaf(p.Gv[1], v[1], p.Gv[0] * v[0])));
+    }
 }
 
 // Work-stealing schedule of the solve: (tile, iteration) units from a global counter.  All per-instance

@@ -238,7 +238,7 @@ def tc_env(env):
         key = (name, mode)
         if key not in packs:
             z, sd = load_golden(name)
-            pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, "phnn")
+            pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, KINDS[name])
             pk.set_option("tensor_min_batch", 0)
             pk.set_option("latency_max_batch", 0)
             pk.set_option("tensor_mode", mode)
@@ -249,7 +249,7 @@ def tc_env(env):
     return ops, get_tc
 
 
-@pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256"])
+@pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256", "canonical"])
 @pytest.mark.parametrize("mode", [3, 1])
 def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
     ops, get_tc = tc_env
@@ -264,11 +264,14 @@ def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
     for integ, iid in (("euler", 0), ("rk4", 1)):
         p = "mpc_%s_" % integ
         tr, _ = ops.rollout(pk.handle, cu(z["mpc_x0"]), cu(np.clip(z["mpc_U0"], lo, hi)), dt, iid, 0)
-        assert rel_err(tr.cpu().numpy(), z[p + "traj0"]) < hor_tol
         cost, g, tr2 = ops.cost_grad(pk.handle, cu(z["mpc_x0"]), cu(z["mpc_U0"]), dt, iid, *ca, True, True)
         assert rel_err(cost.cpu().numpy(), z[p + "hist"][0]) < hor_tol
         assert rel_err(g.cpu().numpy(), z[p + "grad0"]) < grad_tol
-        assert rel_err(tr2.cpu().numpy(), z[p + "traj0"]) < hor_tol
+        if p + "traj0" in z.files:
+            assert rel_err(tr.cpu().numpy(), z[p + "traj0"]) < hor_tol
+            assert rel_err(tr2.cpu().numpy(), z[p + "traj0"]) < hor_tol
+        else:
+            assert rel_err(tr.cpu().numpy(), tr2.cpu().numpy()) < hor_tol
         out = (z["mpc_U0"] < lo) | (z["mpc_U0"] > hi)
         assert np.all(g.cpu().numpy()[out] == 0)
         iters = z[p + "hist"].shape[0]
@@ -281,12 +284,13 @@ def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
 
 
 @pytest.mark.parametrize("B", [1, 127, 129, 700])
-def test_tc_ragged_tiles_vs_oracle(tc_env, B):
+@pytest.mark.parametrize("name", ["cartpole_h256", "canonical"])
+def test_tc_ragged_tiles_vs_oracle(tc_env, B, name):
     """partially filled 128-instance tiles, energies in both orderings, against the CPU oracle"""
     from oracle.phnn_oracle import OracleModel
     ops, get_tc = tc_env
-    z, sd, pk = get_tc("cartpole_h256", 3)
-    M = OracleModel(sd, "phnn")
+    z, sd, pk = get_tc(name, 3)
+    M = OracleModel(sd, KINDS[name])
     rng = np.random.default_rng(B)
     x = (rng.uniform(-1, 1, size=(B, 4)) * [1.0, 0.3, 0.5, 0.5]).astype(np.float32)
     U = rng.uniform(-5, 5, size=(B, 6, 1)).astype(np.float32)
