@@ -154,6 +154,12 @@ __device__ __forceinline__ float dot4(const float4& w, const float (&x)[4], floa
 #endif
 
 // scheduling fence granularity in 4-unit chunks: 4 = one fence per K-block (measured 4.8 % faster than 1)
+#ifndef PHNN_TC_PROD_SLEEP
+#define PHNN_TC_PROD_SLEEP 128
+#endif
+#ifndef PHNN_TC_MMA_SLEEP
+#define PHNN_TC_MMA_SLEEP 128
+#endif
 #ifndef PHNN_TC_FENCE_EVERY
 #define PHNN_TC_FENCE_EVERY 4
 #endif
@@ -223,8 +229,12 @@ struct TcCtx {
 #ifdef PHNN_TC_PROFILE
         const long long t1 = clock64();
 #endif
+#ifdef PHNN_TC_ARRIVE_ALL
+        mbar_arrive(&bars()[SH::B_AFULL + slot]);
+#else
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars()[SH::B_AFULL + slot]);
+#endif
         ++ablk;
 #ifdef PHNN_TC_PROFILE
         const long long t2 = clock64();
@@ -765,8 +775,13 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
+#ifdef PHNN_TC_ARRIVE_ALL
+        mbar_init(&bars[SH::B_AFULL + 0], 256);
+        mbar_init(&bars[SH::B_AFULL + 1], 256);
+#else
         mbar_init(&bars[SH::B_AFULL + 0], 8);
         mbar_init(&bars[SH::B_AFULL + 1], 8);
+#endif
         mbar_init(&bars[SH::B_AEMPTY + 0], 1);
         mbar_init(&bars[SH::B_AEMPTY + 1], 1);
         for (int e = 0; e < SH::NBE; ++e) {
@@ -857,10 +872,10 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
                         const uint32_t slot = ablk & 1u;
-                        mbar_wait_sleep(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u, 32);
+                        mbar_wait_sleep(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u, PHNN_TC_MMA_SLEEP);
                         const uint32_t a_hi = a_base + (slot * 2) * SH::A_TILE, a_lo = a_hi + SH::A_TILE;
                         uint32_t e = bent % SH::NBE;
-                        mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, 32);
+                        mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, PHNN_TC_MMA_SLEEP);
                         tc_fence_after();
                         uint32_t b_t = b_base + e * SH::B_TILE;
 #pragma unroll
@@ -875,7 +890,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                         ++bent;
                         if (split == 3) {
                             e = bent % SH::NBE;
-                            mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, 32);
+                            mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, PHNN_TC_MMA_SLEEP);
                             tc_fence_after();
                             b_t = b_base + e * SH::B_TILE;
 #pragma unroll
@@ -911,7 +926,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                     for (int kb = 0; kb < SH::NKB; ++kb) {
                         for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
                             const uint32_t e = bent % SH::NBE;
-                            mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, 128);
+                            mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, PHNN_TC_PROD_SLEEP);
                             mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
                             bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)(kb * 2 + hl) * SH::B_TILE, SH::B_TILE,
                                      &bars[SH::B_BFULL + e]);
