@@ -420,3 +420,87 @@ def test_lat_matches_batched_kernel(lat_env, env):
                 for pk in (pk_lat, pk_fp)]
         assert rel_err(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy()) < HORIZON_TOL
         assert np.abs(outs[0][0].cpu().numpy() - outs[1][0].cpu().numpy()).max() < 0.02 * lr + 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE cfg5 horizons and full-size properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H", [100, 200])
+def test_tc_long_horizons_vs_oracle(tc_env, H):
+    """cfg5 horizons (RK4, h=256) on a 128-instance sub-sample against the CPU oracle: cost, dJ/dU, two Adam steps."""
+    from oracle.phnn_oracle import OracleModel
+    ops, get_tc = tc_env
+    z, sd, pk = get_tc("cartpole_h256", 3)
+    M = OracleModel(sd, "phnn")
+    B = 128
+    g = torch.Generator().manual_seed(H)
+    x0 = ((torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])).numpy()
+    U0 = ((torch.rand(B, H, 1, generator=g) * 2 - 1) * 2).numpy()
+    Q = np.diag([10.0, 200.0, 1.0, 10.0]).astype(np.float32)
+    R = np.array([[0.01]], np.float32)
+    C = M.cost_struct(Q, R, np.zeros(4), -15.0, 15.0)
+    ca = (torch.from_numpy(Q), torch.from_numpy(R), torch.zeros(4), True, -15.0, 15.0, None, None, 1000.0)
+    Jo, go = M.cost_grad(C, x0, U0, 0.02, "rk4")
+    cost, gg, _ = ops.cost_grad(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, True, False)
+    # long horizons amplify rounding (the cart-pole model is unstable): 4*H steps of FP32 arithmetic
+    tol = HORIZON_TOL * (H / 50.0)
+    assert rel_err(cost.cpu().numpy(), Jo) < tol
+    assert rel_err(gg.cpu().numpy(), go) < 5 * tol
+    Uo, histo, _ = M.mpc_solve(C, x0, U0, 0.02, "rk4", lr=0.015, iters=2)
+    U, hist, _ = ops.mpc_solve(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, 0.015, 0.9, 0.999, 1e-8, 2, 0, True)
+    assert rel_err(hist.cpu().numpy(), histo) < tol
+    assert np.abs(U.cpu().numpy() - Uo).max() < 0.05 * 0.015
+
+
+def test_full_size_properties_cfg4(tc_env):
+    """BASELINE cfg4 batch size (65 536 instances, h=256) through size-independent properties: sharding and
+    permutation invariance (bit for bit: instances are independent and every reduction order is fixed), bounded
+    controls, monotone best cost, zero-iteration solve."""
+    ops, get_tc = tc_env
+    z, sd, pk = get_tc("cartpole_h256", 3)
+    B, H, iters = 65536, 8, 3
+    g = torch.Generator().manual_seed(4)
+    x0 = ((torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])).cuda()
+    U0 = ((torch.rand(B, H, 1, generator=g) * 2 - 1) * 20).cuda()
+    Q = torch.diag(torch.tensor([10.0, 200.0, 1.0, 10.0]))
+    ca = (Q, torch.tensor([[0.01]]), torch.zeros(4), True, -15.0, 15.0, None, None, 1000.0)
+    solve = lambda x, U, it=iters, mode=1: ops.mpc_solve(pk.handle, x, U, 0.02, 1, *ca, 0.015, 0.9, 0.999, 1e-8, it, mode, True)
+    U, hist, best = solve(x0, U0)
+    assert torch.isfinite(U).all() and U.abs().max() <= 15.0
+    assert torch.equal(best, hist.min(0).values)                       # best = min over the cost history
+    # shards solved separately == the full batch (what the multi-GPU path relies on)
+    cut = 40000                                                        # not a multiple of the 128-instance tile
+    Ua, ha, ba = solve(x0[:cut].contiguous(), U0[:cut].contiguous())
+    Ub, hb, bb = solve(x0[cut:].contiguous(), U0[cut:].contiguous())
+    assert torch.equal(torch.cat([Ua, Ub]), U) and torch.equal(torch.cat([ba, bb]), best)
+    assert torch.equal(torch.cat([ha, hb], 1), hist)
+    # permutation of the instances permutes the results
+    perm = torch.randperm(B, generator=g).cuda()
+    Up, hp, bp = solve(x0[perm].contiguous(), U0[perm].contiguous())
+    assert torch.equal(Up, U[perm]) and torch.equal(bp, best[perm])
+    # zero iterations: the clamped initial guess (src/mpc_controller.py:203-207)
+    Uz, _, _ = ops.mpc_solve(pk.handle, x0, U0, 0.02, 1, *ca, 0.015, 0.9, 0.999, 1e-8, 0, 0, False)
+    assert torch.equal(Uz, U0.clamp(-15.0, 15.0))
+    # last-iterate mode equals the Adam trajectory's end, and differs from best-iterate only where the last is not best
+    Ul, hl, _ = solve(x0, U0, iters, 0)
+    assert torch.equal(hl, hist)
+
+
+def test_rollout_linearity_in_time_cfg2_size():
+    """BASELINE cfg2 size (4096 pendulum instances, H=100, RK4): a rollout of T steps equals two chained rollouts of T/2
+    (the kernel carries no hidden state between steps), and the energy orderings are consistent."""
+    from phnn_mpc_b200 import ops
+    from phnn_mpc_b200.packing import PackedModel
+    z, sd = load_golden("pendulum")
+    pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, "phnn")
+    g = torch.Generator().manual_seed(1)
+    B, T = 4096, 100
+    x0 = torch.stack([(torch.rand(B, generator=g) * 2 - 1) * np.pi, torch.rand(B, generator=g) * 2 - 1], 1).cuda()
+    U = (torch.rand(B, T, 1, generator=g) * 4 - 2).cuda()
+    tr, en1 = ops.rollout(pk.handle, x0, U, 0.05, 1, 1)
+    _, en2 = ops.rollout(pk.handle, x0, U, 0.05, 1, 2)
+    tra, _ = ops.rollout(pk.handle, x0, U[:, :50].contiguous(), 0.05, 1, 0)
+    trb, _ = ops.rollout(pk.handle, tra[:, -1].contiguous(), U[:, 50:].contiguous(), 0.05, 1, 0)
+    assert torch.equal(tr[:, :51], tra) and torch.equal(tr[:, 50:], trb)
+    assert torch.equal(en1[:, 1:], en2[:, :-1]) and torch.equal(en1[:, 0], en2[:, 0])
+    assert torch.isfinite(tr).all()
