@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphnn_mpc.so")
+# PHNN_MPC_LIB points the binding at another build of the same library (A/B experiments, tools/gpu_ab.sh)
+LIB_PATH = os.environ.get("PHNN_MPC_LIB") or os.path.join(_HERE, "libphnn_mpc.so")
 
 PHNN_KIND_PHNN, PHNN_KIND_CANONICAL = 0, 1
 PHNN_EULER, PHNN_RK4 = 0, 1

@@ -52,6 +52,12 @@ extern "C" const char* phnn_last_error(void) { return g_err; }
 extern "C" int phnn_version(void) { return 100; }
 
 // ---- dispatch over the compiled (model kind, state dim, hidden width) instantiations ----
+#ifdef PHNN_DEV_CFG4  // fast experiment builds (tools/devbuild.sh): only the cfg4 shape
+#define PHNN_SHAPES(X) X(MK_PHNN, 4, 256)
+#define PHNN_TC_SHAPES(X) X(MK_PHNN, 4, 256)
+#define PHNN_LAT_SHAPES(X) X(MK_PHNN, 4, 64)
+#endif
+#ifndef PHNN_SHAPES
 #define PHNN_SHAPES(X) \
     X(MK_PHNN, 4, 64)  \
     X(MK_PHNN, 4, 128) \
@@ -62,13 +68,16 @@ extern "C" int phnn_version(void) { return 100; }
     X(MK_CANON, 4, 64) \
     X(MK_CANON, 4, 128) \
     X(MK_CANON, 4, 256)
+#endif
 
 // shapes with a tcgen05 instantiation (cart-pole pHNN, fixed G)
+#ifndef PHNN_TC_SHAPES
 #define PHNN_TC_SHAPES(X) \
     X(MK_PHNN, 4, 128)    \
     X(MK_PHNN, 4, 256)    \
     X(MK_CANON, 4, 128)   \
     X(MK_CANON, 4, 256)
+#endif
 
 static bool has_tc_shape(int mk, int n, int h) {
 #define X(MK, NS, HID) \
@@ -79,6 +88,7 @@ static bool has_tc_shape(int mk, int n, int h) {
 }
 
 // shapes with a latency-kernel instantiation (W2 and W2^T must fit in shared memory: h <= 128)
+#ifndef PHNN_LAT_SHAPES
 #define PHNN_LAT_SHAPES(X) \
     X(MK_PHNN, 4, 64)      \
     X(MK_PHNN, 4, 128)     \
@@ -87,6 +97,7 @@ static bool has_tc_shape(int mk, int n, int h) {
     X(MK_PHNN_GNET, 4, 128) \
     X(MK_CANON, 4, 64)     \
     X(MK_CANON, 4, 128)
+#endif
 
 static bool has_lat_shape(int mk, int n, int h) {
 #define X(MK, NS, HID) \
@@ -368,7 +379,7 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     if (P.mode == MODE_SOLVE && P.iters > 0 && P.ws && !no_steal) {
         // work-stealing solve: persistent CTAs pull (tile, iteration) units; the scheduler words sit after the
         // per-tile regions of the workspace and are zeroed on the stream before the launch
-        const size_t tile_floats = ws_floats_per_tile(SH::NS, P.T, P.S, SH::TM, 2 * SH::HID);
+        const size_t tile_floats = ws_floats_per_tile(SH::NS, P.T, P.S, SH::TM, tc_ws_extra(SH::HID, P.T, P.S));
         P.sched = reinterpret_cast<int*>(P.ws + (size_t)tiles * tile_floats);
         CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
         if (grid > pk->num_sms) grid = pk->num_sms;
@@ -486,7 +497,8 @@ extern "C" size_t phnn_workspace_bytes(const phnn_pack* pk, long B, int T, int i
     if (!pk || B <= 0 || T <= 0) return 0;
     // sized for 128-instance tiles (the tcgen05 kernel); a superset of what 32-instance tiles need
     const size_t tiles = ((size_t)B + 127) / 128;
-    return tiles * ws_floats_per_tile(pk->n, T, integrator == PHNN_RK4 ? 4 : 1, 128, 2 * pk->h) * sizeof(float) +
+    const int S = integrator == PHNN_RK4 ? 4 : 1;
+    return tiles * ws_floats_per_tile(pk->n, T, S, 128, tc_ws_extra(pk->h, T, S)) * sizeof(float) +
            sizeof(int) * (tiles + 4);  // + the work-stealing scheduler words
 }
 

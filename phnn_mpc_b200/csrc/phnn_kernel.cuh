@@ -120,10 +120,15 @@ struct KParams {
 
 // floats of workspace per tile of TW instances: stage states [T*S][NS][TW], Adam m, v and best
 // controls [T][TW] (lane-interleaved so the accesses of a warp coalesce)
-// (+ `extra` floats per instance: the tcgen05 kernel stashes one hidden-layer activation there)
+// (+ `extra` floats per instance: the tcgen05 kernel keeps two hidden-layer activations of the evaluation in
+// flight and the R_net output sums of every forward evaluation there, see tc_ws_extra)
 __host__ __device__ inline size_t ws_floats_per_tile(int NS, int T, int S, int TW, int extra = 0) {
     return (size_t)TW * ((size_t)T * S * NS + 3 * (size_t)T + 1 + (size_t)extra);
 }
+
+// extra workspace floats per instance of the tcgen05 kernel: a1 and a2 stashes (2h) + 12 per evaluation for the
+// symmetrised R_net sums the forward sweep leaves for the adjoint (10 used)
+__host__ __device__ inline int tc_ws_extra(int h, int T, int S) { return 2 * h + 12 * T * S; }
 
 // One unit of work of a job: iteration `it` (1-based) of tile `tile`.  The static schedule hands a
 // CTA the iterations of its own tile in order; the work-stealing schedule of the tcgen05 kernel
@@ -262,7 +267,8 @@ template <class SH>
 struct Ctx {
     static constexpr int NS = SH::NS;
     static constexpr int TW = GI;  // instances per workspace tile
-    static constexpr int WS_EXTRA = 0;
+    __device__ static int ws_extra(const KParams&) { return 0; }
+    __device__ __forceinline__ void set_eval(int) {}
     uint32_t goff;  // float offset of this group's region
     int lane, li, lo, wg, barid, wcol, chunk;
     uint32_t tile;  // ring tiles consumed so far
@@ -981,7 +987,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
     for (int i = 0; i < NS; ++i) x0[i] = valid ? p.x0[b * NS + i] : 0.f;
 
     // workspace of this tile: stage states [E][NS][TW], Adam m/v and best controls [T][TW]
-    float* wsg = p.ws ? p.ws + (size_t)tile * ws_floats_per_tile(NS, T, S, TW, ENG::WS_EXTRA) : nullptr;
+    float* wsg = p.ws ? p.ws + (size_t)tile * ws_floats_per_tile(NS, T, S, TW, ENG::ws_extra(p)) : nullptr;
     float* ckpt = wsg;
     float* adam_m = wsg ? wsg + (size_t)E * NS * TW : nullptr;
     float* adam_v = adam_m ? adam_m + (size_t)T * TW : nullptr;
@@ -1033,6 +1039,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
 #pragma unroll
                     for (int i = 0; i < NS; ++i) ckpt[((size_t)(t * S + s) * NS + i) * TW + slot] = ys[i];
                 }
+                c.set_eval(t * S + s);
                 c.eval_fwd(p, ys, u, k, Hv);
                 if (p.mode == MODE_FORWARD) {
                     if (st) {
@@ -1136,6 +1143,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
                         for (int i = 0; i < NS; ++i) kb[i] = fmaf(p.dt6, lam[i], p.dt2 * xb[i]);
                     }
                 }
+                c.set_eval(t * S + s);
                 c.eval_vjp(p, y, u, kb, xb, ub);
                 if (one_vjp) {
                     if (st) {

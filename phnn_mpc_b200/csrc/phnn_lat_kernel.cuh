@@ -60,7 +60,8 @@ template <class SH>
 struct LatCtx {
     static constexpr int NS = SH::NS;
     static constexpr int TW = 1;
-    static constexpr int WS_EXTRA = 0;
+    __device__ static int ws_extra(const KParams&) { return 0; }
+    __device__ __forceinline__ void set_eval(int) {}
     int k, lane, warp;
     bool store;
     // this hidden unit's rows of the small layers

@@ -72,6 +72,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+#ifdef PHNN_TC_EXP_NOMMA  // timing experiment (wrong results): element-side time alone
+    return;
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
@@ -175,12 +178,15 @@ template <class SH>
 struct TcCtx {
     static constexpr int NS = SH::NS;
     static constexpr int TW = SH::TM;
-    static constexpr int WS_EXTRA = 2 * SH::HID;  // a1 and a2 stashes
+    __device__ static int ws_extra(const KParams& p) { return tc_ws_extra(SH::HID, p.T, p.S); }
+    __device__ __forceinline__ void set_eval(int e) { ev = e; }
     int row, hf, lane, barid;
     uint32_t tlane;  // TMEM base address with this warp's lane quadrant
     uint32_t ablk;   // A K-blocks produced so far
     uint32_t qdone;  // products whose accumulator this thread has waited for
     int split;       // 3 = 3xTF32, 1 = plain TF32
+    float* sck;      // R_net sums of every forward evaluation of this tile: [T*S][12][128]
+    int ev;          // index of the evaluation in flight (t * S + s)
     float* stash;    // activation stashes of this tile in the workspace (a2 then a1), each [NKB][2][4][128] float4,
                      // so a warp's 32 rows read/write 512 contiguous bytes
     bool store;
@@ -225,7 +231,9 @@ struct TcCtx {
         const long long t0 = clock64();
 #endif
         tc_fence_before();                                            // earlier tcgen05.ld of this thread are ordered first
+#ifndef PHNN_TC_EXP_NOFENCE  // timing experiment (unsafe): cost of the MEMBAR.ALL.CTA the proxy fence lowers to
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
+#endif
 #ifdef PHNN_TC_PROFILE
         const long long t1 = clock64();
 #endif
@@ -270,8 +278,9 @@ struct TcCtx {
         gbar();
     }
     __device__ __forceinline__ void begin_unit(const KParams& p, long long tile) {
-        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, TW, WS_EXTRA);
+        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, TW, ws_extra(p));
         stash = p.ws ? p.ws + (size_t)tile * tile_floats + ws_floats_per_tile(NS, p.T, p.S, TW, 0) : nullptr;
+        sck = stash ? stash + (size_t)2 * SH::HID * TW : nullptr;
     }
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[4], float u, float (&f)[4], float& H) {
         tc_eval_fwd(*this, p, y, u, f, H);
@@ -305,7 +314,7 @@ __device__ __forceinline__ void tc_acc_S(const float* rC, int k, float r, float*
 
 // phase A of both evaluations: a1 = tanh(W1 y + b1) -> A ring (product z2 = W2 a1), and the
 // R_net hidden layer with its symmetrised output sums
-template <bool STASH, class SH>
+template <bool STASH, bool WITH_R, class SH>
 __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], const float (&y)[4], float* Sp) {
     const float* rA = c.small() + SH::O_RA;
     const float* rB = c.small() + SH::O_RB;
@@ -313,6 +322,7 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
 #pragma unroll 1
     for (int kb = 0; kb < SH::NKB; ++kb) {
         const int slot = c.a_begin();
+        float4 keep[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float av[4];
@@ -321,16 +331,22 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
                 const int k = kb * 32 + c.hf * 16 + q * 4 + e;
                 const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
                 av[e] = tanh_tc(dot4(w1, z, m.x));
-                if constexpr (SH::HAS_R) {
+                if constexpr (SH::HAS_R && WITH_R) {
                     const float r = tanh_tc(dot4(lds4(rB + k * 4), y, m.w));
                     tc_acc_S(rC, k, r, Sp);
                 }
             }
-            if (STASH) *c.stash4(1, kb, q) = make_float4(av[0], av[1], av[2], av[3]);
+            if (STASH) keep[q] = make_float4(av[0], av[1], av[2], av[3]);
             c.a_put4(slot, q, av);
             if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
         }
         c.a_end(slot);
+        // the global stash stores go out after the hand-off: issued before it, the proxy fence of a_end
+        // waits for them to drain (measured: the stashing phases ran 2x slower than their arithmetic)
+        if (STASH) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *c.stash4(1, kb, q) = keep[q];
+        }
     }
 }
 
@@ -371,7 +387,7 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) z[i] = y[i];
     }
-    tc_phase_a1<false>(c, z, y, X);
+    tc_phase_a1<false, true>(c, z, y, X);
 #ifdef PHNN_TC_PROFILE
     c.aphase = 1;
 #endif
@@ -424,6 +440,13 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
     TCP_MARK(c, 4);
     c.exchange(X);
     TCP_MARK(c, 5);
+    if constexpr (SH::HAS_R) {
+        // the adjoint evaluation at this stage state reuses the R_net sums instead of recomputing them
+        if (c.sck && c.store) {
+#pragma unroll
+            for (int i = 0; i < SH::NSYM; ++i) c.sck[((size_t)c.ev * 12 + i) * 128 + c.row] = X[i];
+        }
+    }
     Hval = X[12] + p.b3;
     if constexpr (SH::MK == MK_CANON) {
         float pd[2];
@@ -492,10 +515,14 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) z[i] = y[i];
     }
-    tc_phase_a1<true>(c, z, y, Sp);
+    if constexpr (SH::HAS_R) {
+        // R_net sums left by the forward sweep for this evaluation (ld.cg: written by the partner thread)
+#pragma unroll
+        for (int i = 0; i < SH::NSYM; ++i) Sp[i] = __ldcg(c.sck + ((size_t)c.ev * 12 + i) * 128 + c.row);
+    }
+    tc_phase_a1<true, false>(c, z, y, Sp);
     TCP_MARK(c, 6);
     if constexpr (SH::HAS_R) {
-        c.exchange(Sp);
         tc_make_S(p, Sp, S);
 #pragma unroll
         for (int a = 0; a < 4; ++a) sv[a] = fmaf(S[a][3], v[3], fmaf(S[a][2], v[2], fmaf(S[a][1], v[1], S[a][0] * v[0])));
@@ -516,6 +543,7 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
         TCP_MARK(c, 7);
         for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&zr)[16]) {
             const int slot = c.a_begin();
+            float4 keep[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float dv[4], a2v[4];
@@ -527,11 +555,13 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
                     a2v[e] = a2;
                     dv[e] = fmaf(-a2, a2, 1.f) * m.z;
                 }
-                *c.stash4(0, jb, q) = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
+                keep[q] = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
                 c.a_put4(slot, q, dv);
                 if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
             }
             c.a_end(slot);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *c.stash4(0, jb, q) = keep[q];  // after the hand-off, see tc_phase_a1
         });
     }
     TCP_MARK(c, 8);
@@ -834,6 +864,8 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         c.split = split;
         c.store = (c.hf == 0);
         c.stash = nullptr;
+        c.sck = nullptr;
+        c.ev = 0;
         mbar_wait(&bars[SH::B_SMALL], 0);
 #ifdef PHNN_TC_PROFILE
         for (int i = 0; i < 16; ++i) c.prof[i] = 0;
@@ -927,6 +959,9 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                         for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
                             const uint32_t e = bent % SH::NBE;
                             mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, PHNN_TC_PROD_SLEEP);
+#if defined(PHNN_TC_EXP_NOB)  // timing experiment (wrong results): no weight traffic at all / none for the lo tiles
+                            if (PHNN_TC_EXP_NOB == 2 || hl == 1) { mbar_arrive(&bars[SH::B_BFULL + e]); ++bent; continue; }
+#endif
                             mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
                             bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)(kb * 2 + hl) * SH::B_TILE, SH::B_TILE,
                                      &bars[SH::B_BFULL + e]);

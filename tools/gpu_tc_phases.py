@@ -10,6 +10,7 @@ from phnn_mpc_b200.batched import BatchedMPC, CostSpec
 z, sd = load_golden("cartpole_h256")
 pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, "phnn")
 pk.set_option("tensor_min_batch", 0)
+if os.environ.get("PHNN_TMODE"): pk.set_option("tensor_mode", int(os.environ["PHNN_TMODE"]))
 dbg = torch.zeros(48, dtype=torch.int64, device="cuda")
 L = _lib.lib(); L.phnn_debug_set_buffer.argtypes = [ctypes.c_void_p]; L.phnn_debug_set_buffer(ctypes.c_void_p(dbg.data_ptr()))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128
