@@ -364,8 +364,28 @@ static int launch_lat_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream
     return 0;
 }
 
+// Workspace of a job with an adjoint on the tcgen05 kernel (floats unless noted):
+//   [tiles x ws_floats_per_tile(.., tc_ws_extra)]  stage states, Adam moments, best controls, R_net sums / grad H
+//   [tiles + 4 ints, padded to 16 bytes]            work-stealing scheduler words
+//   [grid x T*S x 3 x h x 128]                      activation tape, one region per CTA (grid = min(tiles, SMs))
+struct TcWorkspace {
+    size_t tile_floats, sched_off, tape_off, bytes;
+    long long tiles, grid;
+};
+static TcWorkspace tc_workspace(const phnn_pack* pk, long long B, int T, int S) {
+    TcWorkspace w;
+    w.tiles = (B + 127) / 128;
+    w.grid = w.tiles < pk->num_sms ? w.tiles : pk->num_sms;
+    w.tile_floats = ws_floats_per_tile(pk->n, T, S, 128, tc_ws_extra(pk->h, T, S));
+    w.sched_off = (size_t)w.tiles * w.tile_floats * sizeof(float);
+    w.tape_off = (w.sched_off + sizeof(int) * (size_t)(w.tiles + 4) + 127) / 128 * 128;
+    w.bytes = w.tape_off + (size_t)w.grid * T * S * 3 * pk->h * 128 * sizeof(float);
+    return w;
+}
+
 template <class SH>
 static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
+    static_assert((3 * SH::HID * 128 * 4) % 65536 == 0, "tape prefetch granularity");
     const long long tiles = (P.B + SH::TM - 1) / SH::TM;
     auto kern = phnn_tc_kernel<SH::MK, SH::NS, SH::HID>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
@@ -374,15 +394,21 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     P.dbg = g_dbg;
     P.tiles = tiles;
     P.sched = nullptr;
+    P.tape = nullptr;
     long long grid = tiles;
     static const bool no_steal = getenv("PHNN_NO_STEAL") != nullptr;  // experiment switch
-    if (P.mode == MODE_SOLVE && P.iters > 0 && P.ws && !no_steal) {
-        // work-stealing solve: persistent CTAs pull (tile, iteration) units; the scheduler words sit after the
-        // per-tile regions of the workspace and are zeroed on the stream before the launch
-        const size_t tile_floats = ws_floats_per_tile(SH::NS, P.T, P.S, SH::TM, tc_ws_extra(SH::HID, P.T, P.S));
-        P.sched = reinterpret_cast<int*>(P.ws + (size_t)tiles * tile_floats);
-        CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
-        if (grid > pk->num_sms) grid = pk->num_sms;
+    const bool adjoint = (P.mode == MODE_SOLVE && P.iters > 0) || (P.mode == MODE_COSTGRAD && P.want_grad);
+    if (adjoint) {
+        // the forward sweep tapes its activations into a per-CTA region: at most one CTA per SM, each running
+        // its tiles one after the other (static stride) or pulling (tile, iteration) units (work-stealing solve)
+        if (!P.ws) return fail(PHNN_E_WORKSPACE, "tcgen05 path: a job with an adjoint needs the workspace");
+        const TcWorkspace w = tc_workspace(pk, P.B, P.T, P.S);
+        grid = w.grid;
+        P.tape = reinterpret_cast<float*>(reinterpret_cast<char*>(P.ws) + w.tape_off);
+        if (P.mode == MODE_SOLVE && !no_steal) {
+            P.sched = reinterpret_cast<int*>(reinterpret_cast<char*>(P.ws) + w.sched_off);
+            CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
+        }
     }
     kern<<<(unsigned)grid, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
@@ -495,11 +521,14 @@ extern "C" int phnn_rollout(const phnn_pack* pk, const float* x0, const float* U
 
 extern "C" size_t phnn_workspace_bytes(const phnn_pack* pk, long B, int T, int integrator) {
     if (!pk || B <= 0 || T <= 0) return 0;
-    // sized for 128-instance tiles (the tcgen05 kernel); a superset of what 32-instance tiles need
-    const size_t tiles = ((size_t)B + 127) / 128;
     const int S = integrator == PHNN_RK4 ? 4 : 1;
-    return tiles * ws_floats_per_tile(pk->n, T, S, 128, tc_ws_extra(pk->h, T, S)) * sizeof(float) +
-           sizeof(int) * (tiles + 4);  // + the work-stealing scheduler words
+    // the tcgen05 kernel's layout (128-instance tiles + scheduler words + activation tape) when this batch is
+    // routed there; otherwise the per-tile part alone, a superset of what the 32-instance tiles of the FP32
+    // kernel and the single-instance tiles of the latency kernel use
+    const bool lat = pk->lat_max_batch > 0 && B <= pk->lat_max_batch && has_lat_shape(pk->mk, pk->n, pk->h);
+    const bool tc = !lat && pk->tc_mode != 0 && pk->d_wtc && B >= pk->tc_min_batch;
+    const TcWorkspace w = tc_workspace(pk, B, T, S);
+    return tc ? w.bytes : w.tape_off;
 }
 
 extern "C" int phnn_cost_grad(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, const float* U,

@@ -114,21 +114,22 @@ struct KParams {
     float* cost_hist;  // SOLVE [iters,B] (nullable)
     float* ws;         // workspace
     int* sched;        // work-stealing solve (tcgen05 kernel): [0] unit counter, [1 + tile] iterations completed
-    long long tiles;   // number of 128-instance tiles (work-stealing solve)
+    long long tiles;   // number of 128-instance tiles (tcgen05 kernel)
+    float* tape;       // tcgen05 kernel: activation tape, [grid][T*S][3][h][128] floats (jobs with an adjoint)
     long long* dbg;    // optional profiling output (PHNN_TC_PROFILE builds)
 };
 
 // floats of workspace per tile of TW instances: stage states [T*S][NS][TW], Adam m, v and best
 // controls [T][TW] (lane-interleaved so the accesses of a warp coalesce)
-// (+ `extra` floats per instance: the tcgen05 kernel keeps two hidden-layer activations of the evaluation in
-// flight and the R_net output sums of every forward evaluation there, see tc_ws_extra)
+// (+ `extra` floats per instance: the tcgen05 kernel keeps the R_net output sums and grad H of every forward
+// evaluation there, see tc_ws_extra; its activation tape is a separate per-CTA region, see phnn_capi.cu)
 __host__ __device__ inline size_t ws_floats_per_tile(int NS, int T, int S, int TW, int extra = 0) {
     return (size_t)TW * ((size_t)T * S * NS + 3 * (size_t)T + 1 + (size_t)extra);
 }
 
-// extra workspace floats per instance of the tcgen05 kernel: a1 and a2 stashes (2h) + 12 per evaluation for the
-// symmetrised R_net sums the forward sweep leaves for the adjoint (10 used)
-__host__ __device__ inline int tc_ws_extra(int h, int T, int S) { return 2 * h + 12 * T * S; }
+// extra workspace floats per instance of the tcgen05 kernel: 16 per evaluation for the symmetrised R_net sums
+// (10) and grad H (4) the forward sweep leaves for the adjoint
+__host__ __device__ inline int tc_ws_extra(int /*h*/, int T, int S) { return 16 * T * S; }
 
 // One unit of work of a job: iteration `it` (1-based) of tile `tile`.  The static schedule hands a
 // CTA the iterations of its own tile in order; the work-stealing schedule of the tcgen05 kernel
@@ -1008,7 +1009,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
             ubest[t * TW + slot] = clampu(p, p.U[b * T + t]);
         }
     }
-    float best = best_reg;
+    float best = (it == 1) ? __int_as_float(0x7f800000) : best_reg;
     if (SCHED::kStateInWorkspace) best = (it == 1 || !valid) ? __int_as_float(0x7f800000) : __ldcg(bestws + slot);
 
     {

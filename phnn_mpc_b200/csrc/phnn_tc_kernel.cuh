@@ -23,6 +23,15 @@
 //     instance (tcgen05.ld 32x32b gives a thread its own TMEM lane), so every reduction over
 //     the hidden dimension is a private register loop; the two halves of an instance meet in
 //     one small shared-memory exchange per reduction.
+//   * the forward sweep of a cost/solve job keeps a tape: a1, a2 and g1 = W2^T(s2 * w3) of every
+//     evaluation go to a per-CTA region of the workspace (HBM; 3 h floats per instance and
+//     evaluation), together with the R_net sums and grad H.  The adjoint evaluation then needs
+//     only the two Hessian-vector products (dz2 = W2 da1, dg1 = W2^T e2) instead of recomputing
+//     z2 and g1 first: 4 tensor products per (forward, adjoint) pair instead of 6.  The producer
+//     warp prefetches the tape of the next adjoint evaluation into L2 (cp.async.bulk.prefetch).
+//   * element work that does not feed the tensor pipe is folded into the phases that do (their
+//     K-block loops wait for the MMA most of the time): the g1 half of xbar and half of the R_net
+//     backward chain ride in the da1 loop, the other half of the R_net chain in the e2 loop.
 //
 // Roles: warps 0-7 element threads (256), warp 8 MMA issuer (one lane), warp 9 weight producer.
 #pragma once
@@ -185,10 +194,10 @@ struct TcCtx {
     uint32_t ablk;   // A K-blocks produced so far
     uint32_t qdone;  // products whose accumulator this thread has waited for
     int split;       // 3 = 3xTF32, 1 = plain TF32
-    float* sck;      // R_net sums of every forward evaluation of this tile: [T*S][12][128]
+    float* sck;      // per tile: R_net sums [0,10) and grad H [10,14) of every forward evaluation, [T*S][16][128]
     int ev;          // index of the evaluation in flight (t * S + s)
-    float* stash;    // activation stashes of this tile in the workspace (a2 then a1), each [NKB][2][4][128] float4,
-                     // so a warp's 32 rows read/write 512 contiguous bytes
+    float* tape;     // per CTA: a2, a1, g1 of every forward evaluation of the unit in flight, each [NKB][2][4][128]
+                     // float4 (a warp's 32 rows read/write 512 contiguous bytes); nullptr when no adjoint follows
     bool store;
 #ifdef PHNN_TC_PROFILE
     long long prof[16];
@@ -257,13 +266,14 @@ struct TcCtx {
         tc_fence_after();
         return tlane + (q & 1u) * SH::HID + hf * 16;
     }
-    // float4 slot of (stash which, K-block jb, chunk q) for this thread
-    __device__ __forceinline__ float4* stash4(int which, int jb, int q) const {
-        return reinterpret_cast<float4*>(stash) + ((size_t)which * SH::NKB * 8 + (jb * 2 + hf) * 4 + q) * 128 + row;
+    // float4 slot of (tape array which: 0 a2, 1 a1, 2 g1; K-block jb; chunk q) of evaluation ev for this thread
+    static constexpr size_t TAPE_ARR4 = (size_t)SH::NKB * 8 * 128;  // float4 per array
+    __device__ __forceinline__ float4* tape4(int which, int jb, int q) const {
+        return reinterpret_cast<float4*>(tape) + ((size_t)ev * 3 + which) * TAPE_ARR4 + ((jb * 2 + hf) * 4 + q) * 128 + row;
     }
-    __device__ __forceinline__ void stash_load(int which, int jb, float4 (&v)[4]) const {
+    __device__ __forceinline__ void tape_load(int which, int jb, float4 (&v)[4]) const {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = __ldcg(stash4(which, jb, q));
+        for (int q = 0; q < 4; ++q) v[q] = __ldcg(tape4(which, jb, q));
     }
     // pair exchange: returns mine + partner's for n values starting at slot s0
     template <int N>
@@ -279,8 +289,7 @@ struct TcCtx {
     }
     __device__ __forceinline__ void begin_unit(const KParams& p, long long tile) {
         const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, TW, ws_extra(p));
-        stash = p.ws ? p.ws + (size_t)tile * tile_floats + ws_floats_per_tile(NS, p.T, p.S, TW, 0) : nullptr;
-        sck = stash ? stash + (size_t)2 * SH::HID * TW : nullptr;
+        sck = p.ws ? p.ws + (size_t)tile * tile_floats + ws_floats_per_tile(NS, p.T, p.S, TW, 0) : nullptr;
     }
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[4], float u, float (&f)[4], float& H) {
         tc_eval_fwd(*this, p, y, u, f, H);
@@ -312,9 +321,9 @@ __device__ __forceinline__ void tc_acc_S(const float* rC, int k, float r, float*
     Sp[8] = fmaf(c2.x, r, Sp[8]); Sp[9] = fmaf(c2.y, r, Sp[9]);
 }
 
-// phase A of both evaluations: a1 = tanh(W1 y + b1) -> A ring (product z2 = W2 a1), and the
-// R_net hidden layer with its symmetrised output sums
-template <bool STASH, bool WITH_R, class SH>
+// phase A of the forward evaluation: a1 = tanh(W1 y + b1) -> A ring (product z2 = W2 a1) and the tape,
+// and the R_net hidden layer with its symmetrised output sums
+template <class SH>
 __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], const float (&y)[4], float* Sp) {
     const float* rA = c.small() + SH::O_RA;
     const float* rB = c.small() + SH::O_RB;
@@ -322,7 +331,6 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
 #pragma unroll 1
     for (int kb = 0; kb < SH::NKB; ++kb) {
         const int slot = c.a_begin();
-        float4 keep[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float av[4];
@@ -331,22 +339,16 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
                 const int k = kb * 32 + c.hf * 16 + q * 4 + e;
                 const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
                 av[e] = tanh_tc(dot4(w1, z, m.x));
-                if constexpr (SH::HAS_R && WITH_R) {
+                if constexpr (SH::HAS_R) {
                     const float r = tanh_tc(dot4(lds4(rB + k * 4), y, m.w));
                     tc_acc_S(rC, k, r, Sp);
                 }
             }
-            if (STASH) keep[q] = make_float4(av[0], av[1], av[2], av[3]);
+            if (c.tape) *c.tape4(1, kb, q) = make_float4(av[0], av[1], av[2], av[3]);
             c.a_put4(slot, q, av);
             if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
         }
         c.a_end(slot);
-        // the global stash stores go out after the hand-off: issued before it, the proxy fence of a_end
-        // waits for them to drain (measured: the stashing phases ran 2x slower than their arithmetic)
-        if (STASH) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) *c.stash4(1, kb, q) = keep[q];
-        }
     }
 }
 
@@ -387,7 +389,7 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) z[i] = y[i];
     }
-    tc_phase_a1<false, true>(c, z, y, X);
+    tc_phase_a1(c, z, y, X);
 #ifdef PHNN_TC_PROFILE
     c.aphase = 1;
 #endif
@@ -401,15 +403,17 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
             const int slot = c.a_begin();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float dv[4];
+                float dv[4], a2v[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = jb * 32 + c.hf * 16 + q * 4 + e;
                     const float4 m = lds4(rA + j * 8 + 4);
                     const float a2 = tanh_tc(__uint_as_float(zr[q * 4 + e]) + m.y);
+                    a2v[e] = a2;
                     Hp = fmaf(m.z, a2, Hp);
                     dv[e] = fmaf(-a2, a2, 1.f) * m.z;
                 }
+                if (c.tape) *c.tape4(0, jb, q) = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
                 c.a_put4(slot, q, dv);
                 if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
             }
@@ -424,6 +428,12 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
         TCP_MARK(c, 3);
         float g0 = 0.f, g1s = 0.f, g2 = 0.f, g3 = 0.f;
         for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
+            if (c.tape) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *c.tape4(2, kb, q) = make_float4(__uint_as_float(gr[q * 4]), __uint_as_float(gr[q * 4 + 1]),
+                                                     __uint_as_float(gr[q * 4 + 2]), __uint_as_float(gr[q * 4 + 3]));
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int k = kb * 32 + c.hf * 16 + i;
@@ -440,12 +450,14 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
     TCP_MARK(c, 4);
     c.exchange(X);
     TCP_MARK(c, 5);
-    if constexpr (SH::HAS_R) {
-        // the adjoint evaluation at this stage state reuses the R_net sums instead of recomputing them
-        if (c.sck && c.store) {
+    if (c.tape && c.store) {
+        // the adjoint evaluation at this stage state reuses the R_net sums and grad H
+        if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int i = 0; i < SH::NSYM; ++i) c.sck[((size_t)c.ev * 12 + i) * 128 + c.row] = X[i];
+            for (int i = 0; i < SH::NSYM; ++i) c.sck[((size_t)c.ev * 16 + i) * 128 + c.row] = X[i];
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.sck[((size_t)c.ev * 16 + 10 + i) * 128 + c.row] = X[13 + i];
     }
     Hval = X[12] + p.b3;
     if constexpr (SH::MK == MK_CANON) {
@@ -474,27 +486,43 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
 }
 
 // ---------------------------------------------------------------------------------------
-// xbar = (df/dy)^T v, ubar = (df/du)^T v with recomputed activations and the Hessian-vector
-// product of H_net.  Product order: z2 -> acc0, g1 -> acc1, dz2 -> acc0, dg1 -> acc1.
+// xbar = (df/dy)^T v, ubar = (df/du)^T v from the taped activations of the forward evaluation
+// at the same stage state and the Hessian-vector product of H_net.
+// Products: dz2 = W2 da1 -> acc0, dg1 = W2^T e2 -> acc1.
 // ---------------------------------------------------------------------------------------
+// R_net backward chain for one hidden unit: xbar += Wr1[k]^T (1 - r^2) (Wr2sym[k] . Rb)
+template <class SH>
+__device__ __forceinline__ void tc_rback_unit(const TcCtx<SH>& c, int k, const float (&y)[4], const float (&Rb)[12], float (&X4)[4]) {
+    const float* rA = c.small() + SH::O_RA;
+    const float* rB = c.small() + SH::O_RB;
+    const float* rC = c.small() + SH::O_RC;
+    const float4 c0 = lds4(rC + k * 12), c1 = lds4(rC + k * 12 + 4);
+    const float2 c2 = *reinterpret_cast<const float2*>(rC + k * 12 + 8);
+    float rb = c0.x * Rb[0];
+    rb = fmaf(c0.y, Rb[1], rb); rb = fmaf(c0.z, Rb[2], rb); rb = fmaf(c0.w, Rb[3], rb);
+    rb = fmaf(c1.x, Rb[4], rb); rb = fmaf(c1.y, Rb[5], rb); rb = fmaf(c1.z, Rb[6], rb); rb = fmaf(c1.w, Rb[7], rb);
+    rb = fmaf(c2.x, Rb[8], rb); rb = fmaf(c2.y, Rb[9], rb);
+    const float4 wr = lds4(rB + k * 4);
+    const float r1 = tanh_tc(dot4(wr, y, rA[k * 8 + 7]));
+    const float zb = rb * fmaf(-r1, r1, 1.f);
+    X4[0] = fmaf(wr.x, zb, X4[0]); X4[1] = fmaf(wr.y, zb, X4[1]); X4[2] = fmaf(wr.z, zb, X4[2]); X4[3] = fmaf(wr.w, zb, X4[3]);
+}
+
 template <class SH>
 __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u,
                                          const float (&v)[4], float (&xbar)[4], float& ubar) {
     constexpr int NKB = SH::NKB;
     const float* rA = c.small() + SH::O_RA;
-    const float* rB = c.small() + SH::O_RB;
-    const float* rC = c.small() + SH::O_RC;
-    float Sp[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) Sp[i] = 0.f;
-    // ---- A1: a1 -> product 1 ; R_net forward sums ----
     TCP_MARK(c, 15);
 #ifdef PHNN_TC_PROFILE
     c.aphase = 2;
 #endif
-    float z[4], w[4], S[4][4], sv[4];
+    float z[4], w[4], G4[4], sv[4], Rb[12];
     Canon cq = {};
     float pb[2] = {0.f, 0.f}, pdb[2] = {0.f, 0.f};
+    // grad H of the forward evaluation at this stage state (ld.cg: written by the partner thread)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) G4[i] = __ldcg(c.sck + ((size_t)c.ev * 16 + 10 + i) * 128 + c.row);
     if constexpr (SH::MK == MK_CANON) {
         cq = canon_of(p, y[1]);
         z[0] = y[0]; z[1] = y[1];
@@ -516,13 +544,9 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
         for (int i = 0; i < 4; ++i) z[i] = y[i];
     }
     if constexpr (SH::HAS_R) {
-        // R_net sums left by the forward sweep for this evaluation (ld.cg: written by the partner thread)
+        float Sp[12], S[4][4], tg[4];
 #pragma unroll
-        for (int i = 0; i < SH::NSYM; ++i) Sp[i] = __ldcg(c.sck + ((size_t)c.ev * 12 + i) * 128 + c.row);
-    }
-    tc_phase_a1<true, false>(c, z, y, Sp);
-    TCP_MARK(c, 6);
-    if constexpr (SH::HAS_R) {
+        for (int i = 0; i < SH::NSYM; ++i) Sp[i] = __ldcg(c.sck + ((size_t)c.ev * 16 + i) * 128 + c.row);
         tc_make_S(p, Sp, S);
 #pragma unroll
         for (int a = 0; a < 4; ++a) sv[a] = fmaf(S[a][3], v[3], fmaf(S[a][2], v[2], fmaf(S[a][1], v[1], S[a][0] * v[0])));
@@ -535,112 +559,71 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
             for (int b = 0; b < 4; ++b) s = fmaf(-S[a][b], sv[b], s);
             w[a] = s;
         }
+        // cotangent of S: -(v t^T + g s^T) symmetrised, packed with multiplicity 2 off the diagonal
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tg[a] = fmaf(S[a][3], G4[3], fmaf(S[a][2], G4[2], fmaf(S[a][1], G4[1], S[a][0] * G4[0])));
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b)
+                Rb[sym_idx(a, b)] = (a == b ? -0.5f : -1.0f) * (v[a] * tg[b] + G4[a] * sv[b] + v[b] * tg[a] + G4[b] * sv[a]);
+        Rb[10] = 0.f; Rb[11] = 0.f;
     }
-    // ---- B1: a2 (stashed), delta2 -> product 2 ----
+    float X4[4] = {0.f, 0.f, 0.f, 0.f};  // xbar partial over my hidden units
+    // ---- A3: da1 = s1 * (W1 w) -> product 1 (dz2 = W2 da1), with the g1 half of xbar_H (sdot1 * g1) and the
+    //      first half of the R_net chain in the same loop (the loop runs at the pace of the MMA) ----
     {
-        TCP_MARK(c, 5);
-        const uint32_t tacc = c.acc_wait();
-        TCP_MARK(c, 7);
-        for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&zr)[16]) {
-            const int slot = c.a_begin();
-            float4 keep[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float dv[4], a2v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = jb * 32 + c.hf * 16 + q * 4 + e;
-                    const float4 m = lds4(rA + j * 8 + 4);
-                    const float a2 = tanh_tc(__uint_as_float(zr[q * 4 + e]) + m.y);
-                    a2v[e] = a2;
-                    dv[e] = fmaf(-a2, a2, 1.f) * m.z;
-                }
-                keep[q] = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
-                c.a_put4(slot, q, dv);
-                if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
-            }
-            c.a_end(slot);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) *c.stash4(0, jb, q) = keep[q];  // after the hand-off, see tc_phase_a1
-        });
-    }
-    TCP_MARK(c, 8);
-#ifdef PHNN_TC_PROFILE
-    c.aphase = 4;
-#endif
-    // ---- A3: da1 = s1 * (W1 w) -> product 3 (dz2 = W2 da1); a1 comes back from the stash ----
-    {
-        float4 an[4];
-        c.stash_load(1, 0, an);
+        float4 an[4], gn[4];
+        c.tape_load(1, 0, an);
+        c.tape_load(2, 0, gn);
 #pragma unroll 1
         for (int kb = 0; kb < NKB; ++kb) {
-            float4 ac[4];
+            float4 ac[4], gc[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ac[q] = an[q];
-            if (kb + 1 < NKB) c.stash_load(1, kb + 1, an);
+            for (int q = 0; q < 4; ++q) { ac[q] = an[q]; gc[q] = gn[q]; }
+            if (kb + 1 < NKB) {
+                c.tape_load(1, kb + 1, an);
+                c.tape_load(2, kb + 1, gn);
+            }
             const int slot = c.a_begin();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
+                const float g1v[4] = {gc[q].x, gc[q].y, gc[q].z, gc[q].w};
                 float av[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = kb * 32 + c.hf * 16 + q * 4 + e;
-                    av[e] = fmaf(-a1v[e], a1v[e], 1.f) * dot4(lds4(rA + k * 8), w, 0.f);
-                }
-                c.a_put4(slot, q, av);
-            }
-            c.a_end(slot);
-        }
-    }
-    TCP_MARK(c, 9);
-    // ---- C2: g1 -> dH partial and the g1 half of xbar_H ----
-    float Y[8];  // [0,4) dH partial, [4,8) xbar partial
-#pragma unroll
-    for (int i = 0; i < 8; ++i) Y[i] = 0.f;
-    {
-        float4 an[4];
-        c.stash_load(1, 0, an);
-        const uint32_t tacc = c.acc_wait();
-        TCP_MARK(c, 1);
-        for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
-            float4 ac[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ac[q] = an[q];
-            if (kb + 1 < NKB) c.stash_load(1, kb + 1, an);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int k = kb * 32 + c.hf * 16 + q * 4 + e;
                     const float4 w1 = lds4(rA + k * 8);
                     const float a1 = a1v[e];
-                    const float s1 = fmaf(-a1, a1, 1.f);
-                    const float g1 = __uint_as_float(gr[q * 4 + e]);
-                    const float d1 = s1 * g1;
-                    const float t = -2.f * a1 * (s1 * dot4(w1, w, 0.f)) * g1;
-                    Y[0] = fmaf(w1.x, d1, Y[0]); Y[1] = fmaf(w1.y, d1, Y[1]); Y[2] = fmaf(w1.z, d1, Y[2]); Y[3] = fmaf(w1.w, d1, Y[3]);
-                    Y[4] = fmaf(w1.x, t, Y[4]); Y[5] = fmaf(w1.y, t, Y[5]); Y[6] = fmaf(w1.z, t, Y[6]); Y[7] = fmaf(w1.w, t, Y[7]);
+                    av[e] = fmaf(-a1, a1, 1.f) * dot4(w1, w, 0.f);
+                    const float t = -2.f * a1 * av[e] * g1v[e];
+                    X4[0] = fmaf(w1.x, t, X4[0]); X4[1] = fmaf(w1.y, t, X4[1]); X4[2] = fmaf(w1.z, t, X4[2]); X4[3] = fmaf(w1.w, t, X4[3]);
                 }
+                c.a_put4(slot, q, av);
             }
-        });
+            c.a_end(slot);
+            if constexpr (SH::HAS_R) {
+#pragma unroll 4
+                for (int i = 0; i < 8; ++i) tc_rback_unit(c, kb * 32 + c.hf * 16 + i, y, Rb, X4);
+            }
+        }
     }
-    TCP_MARK(c, 10);
+    TCP_MARK(c, 6);
 #ifdef PHNN_TC_PROFILE
     c.aphase = 5;
 #endif
-    // ---- B3: e2 = -2 a2 da2 w3 -> product 4 (dg1 = W2^T e2) ----
+    // ---- B3: e2 = -2 a2 da2 w3 -> product 2 (dg1 = W2^T e2); second half of the R_net chain ----
     {
-        const uint32_t tacc = c.acc_wait();
-        TCP_MARK(c, 3);
         float4 an[4];
-        c.stash_load(0, 0, an);
+        c.tape_load(0, 0, an);
+        const uint32_t tacc = c.acc_wait();
+        TCP_MARK(c, 7);
         for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&dz)[16]) {
             float4 a2q[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) a2q[q] = an[q];
-            if (jb + 1 < NKB) c.stash_load(0, jb + 1, an);
+            if (jb + 1 < NKB) c.tape_load(0, jb + 1, an);
             const int slot = c.a_begin();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -656,54 +639,24 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
                 c.a_put4(slot, q, ev);
             }
             c.a_end(slot);
+            if constexpr (SH::HAS_R) {
+#pragma unroll 4
+                for (int i = 8; i < 16; ++i) tc_rback_unit(c, jb * 32 + c.hf * 16 + i, y, Rb, X4);
+            }
         });
     }
-    TCP_MARK(c, 11);
-    // ---- while product 4 runs: dH total, then the R_net chain (thread-local over my hidden units) ----
-    float G4[4] = {Y[0], Y[1], Y[2], Y[3]};
-    c.exchange(G4);
-    float X4[4] = {Y[4], Y[5], Y[6], Y[7]};
-    if constexpr (SH::HAS_R) {
-        // cotangent of S: -(v t^T + g s^T) symmetrised, packed with multiplicity 2 off the diagonal
-        float tg[4], Rb[12];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) tg[a] = fmaf(S[a][3], G4[3], fmaf(S[a][2], G4[2], fmaf(S[a][1], G4[1], S[a][0] * G4[0])));
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = a; b < 4; ++b)
-                Rb[sym_idx(a, b)] = (a == b ? -0.5f : -1.0f) * (v[a] * tg[b] + G4[a] * sv[b] + v[b] * tg[a] + G4[b] * sv[a]);
-        Rb[10] = 0.f; Rb[11] = 0.f;
-#pragma unroll 1
-        for (int kk = 0; kk < SH::HID / 2; kk += 4) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = ((kk + e) >> 4) * 32 + c.hf * 16 + ((kk + e) & 15);
-                const float4 c0 = lds4(rC + k * 12), c1 = lds4(rC + k * 12 + 4);
-                const float2 c2 = *reinterpret_cast<const float2*>(rC + k * 12 + 8);
-                float rb = c0.x * Rb[0];
-                rb = fmaf(c0.y, Rb[1], rb); rb = fmaf(c0.z, Rb[2], rb); rb = fmaf(c0.w, Rb[3], rb);
-                rb = fmaf(c1.x, Rb[4], rb); rb = fmaf(c1.y, Rb[5], rb); rb = fmaf(c1.z, Rb[6], rb); rb = fmaf(c1.w, Rb[7], rb);
-                rb = fmaf(c2.x, Rb[8], rb); rb = fmaf(c2.y, Rb[9], rb);
-                const float4 wr = lds4(rB + k * 4);
-                const float r1 = tanh_tc(dot4(wr, y, rA[k * 8 + 7]));
-                const float zb = rb * fmaf(-r1, r1, 1.f);
-                X4[0] = fmaf(wr.x, zb, X4[0]); X4[1] = fmaf(wr.y, zb, X4[1]); X4[2] = fmaf(wr.z, zb, X4[2]); X4[3] = fmaf(wr.w, zb, X4[3]);
-            }
-        }
-    }
-    TCP_MARK(c, 12);
+    TCP_MARK(c, 8);
     // ---- C4: the dg1 half of xbar_H ----
     {
-        const uint32_t tacc = c.acc_wait();
-        TCP_MARK(c, 13);
         float4 an[4];
-        c.stash_load(1, 0, an);
+        c.tape_load(1, 0, an);
+        const uint32_t tacc = c.acc_wait();
+        TCP_MARK(c, 9);
         for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&dg)[16]) {
             float4 ac[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) ac[q] = an[q];
-            if (kb + 1 < NKB) c.stash_load(1, kb + 1, an);
+            if (kb + 1 < NKB) c.tape_load(1, kb + 1, an);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
@@ -718,7 +671,7 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
         });
         tc_fence_before();
     }
-    TCP_MARK(c, 14);
+    TCP_MARK(c, 10);
     c.exchange(X4);
     TCP_MARK(c, 5);
     if constexpr (SH::MK == MK_CANON) {
@@ -795,6 +748,27 @@ struct StealSched {
     }
 };
 
+// Static schedule of the tcgen05 kernel: CTA b runs all iterations of tiles b, b + grid, b + 2 grid, ...
+// (jobs with an adjoint run on at most one CTA per SM because the tape is a per-CTA region)
+struct StridedSched {
+    long long first, tile, tiles;
+    int stride, n_outer, it;
+    static constexpr bool kStateInWorkspace = false;
+    __device__ __forceinline__ long long tile0() const { return first; }
+    __device__ __forceinline__ bool next(Unit& u) {
+        if (it >= n_outer) {
+            tile += stride;
+            it = 0;
+        }
+        if (n_outer <= 0 || tile >= tiles) return false;
+        u.tile = tile;
+        u.it = ++it;
+        return true;
+    }
+    template <class ENG>
+    __device__ __forceinline__ void done(ENG& c, const Unit&) { c.gbar(); }
+};
+
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
@@ -846,8 +820,14 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         default: n_outer = p.iters; nfwd = E; nadj = E; break;
     }
     const bool steal = (p.mode == MODE_SOLVE) && p.sched != nullptr && p.iters > 0;
-    // products per schedule unit: a whole job (static schedule) or one solve iteration (work stealing)
-    const long long nprod = (steal ? 1LL : (long long)n_outer) * (2LL * nfwd + 4LL * nadj);
+    // products per schedule unit (two per evaluation, forward or adjoint): all iterations of a tile (static
+    // schedule) or one solve iteration (work stealing)
+    const long long nprod = (steal ? 1LL : (long long)n_outer) * (2LL * nfwd + 2LL * nadj);
+    const long long per_iter = 2LL * nfwd + 2LL * nadj;
+    // tiles of this CTA under the static schedule
+    const long long my_tiles = p.tiles > (long long)blockIdx.x ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const size_t tape_eval = (size_t)3 * HID * 128;  // floats per taped evaluation
+    float* const tape = (p.tape && nadj > 0) ? p.tape + (size_t)blockIdx.x * E * tape_eval : nullptr;
     const int split = p.tc_split;
     StealSched ss{p.sched, p.sched + 1, p.tiles, p.iters, reinterpret_cast<int*>(phnn_smem + 768)};
 
@@ -863,7 +843,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         c.qdone = 0;
         c.split = split;
         c.store = (c.hf == 0);
-        c.stash = nullptr;
+        c.tape = tape;
         c.sck = nullptr;
         c.ev = 0;
         mbar_wait(&bars[SH::B_SMALL], 0);
@@ -877,7 +857,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         if (steal) {
             run_job(c, p, ss, c.row);
         } else {
-            StaticSched sched{(long long)blockIdx.x, n_outer, 0};
+            StridedSched sched{(long long)blockIdx.x, (long long)blockIdx.x, p.tiles, (int)gridDim.x, n_outer, 0};
             run_job(c, p, sched, c.row);
         }
         tc_fence_before();
@@ -895,8 +875,8 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         const uint32_t a_base = smem_u32(phnn_smem + SH::OFF_A), b_base = smem_u32(phnn_smem + SH::OFF_B);
         uint32_t ablk = 0, bent = 0;
         long long qtot = 0;  // products issued so far (accumulator / operand parity continues across units)
-        for (;;) {
-            if (steal && ss.grab() < 0) break;
+        for (long long unit = 0;; ++unit) {
+            if (steal ? ss.grab() < 0 : unit >= my_tiles) break;
             if (lane == 0) {
 #pragma unroll 1
                 for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
@@ -938,7 +918,6 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                 }
             }
             __syncwarp();
-            if (!steal) break;
         }
     } else {
         // ===== weight producer (TMA bulk copies of pre-swizzled K-blocks) =====
@@ -948,11 +927,24 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         }
         uint32_t bent = 0;
         long long qtot = 0;
-        for (;;) {
-            if (steal && ss.grab() < 0) break;
+        for (long long unit = 0;; ++unit) {
+            if (steal ? ss.grab() < 0 : unit >= my_tiles) break;
             if (lane == 0) {
 #pragma unroll 1
                 for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
+                    if (tape && !(qq & 1)) {
+                        // adjoint evaluations run from the last taped evaluation down: while evaluation e is in
+                        // flight, pull the tape of e - 1 (written a whole sweep ago, so in HBM) into L2
+                        const long long qi = qq % per_iter - 2LL * nfwd;
+                        if (qi >= 0) {
+                            const long long e_next = (long long)E - 2 - (qi >> 1);
+                            if (e_next >= 0) {
+                                const char* src = reinterpret_cast<const char*>(tape + (size_t)e_next * tape_eval);
+                                for (int off = 0; off < (int)(tape_eval * 4); off += 65536)
+                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(65536) : "memory");
+                            }
+                        }
+                    }
                     const unsigned char* src = p.wtc + (size_t)(qtot & 1) * SH::NKB * 2 * SH::B_TILE;
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
@@ -971,7 +963,6 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                 }
             }
             __syncwarp();
-            if (!steal) break;
         }
     }
     __syncthreads();
