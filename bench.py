@@ -331,15 +331,23 @@ def main():
         tr = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
         if tr.get("workload") == args.workload and tr.get("B") == B:
             traffic = tr.get("dram_bytes_per_launch")
+        elif tr.get("h") == h and tr.get("dram_bytes_per_tile_eval_pair") and kind == "phnn":
+            # the capture is of a slice of the same job: DRAM traffic is proportional to (tiles x evaluation pairs)
+            traffic = tr["dram_bytes_per_tile_eval_pair"] * ((B + 127) // 128) * iters * H * S
     except Exception:
         pass
     if uses_tc:
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         split = 3 if tmode == 3 else 1
-        # tensor work actually issued: per evaluation 2 (forward) or 4 (adjoint) products of 128 x h x h MACs per
-        # 128-instance tile, each as `split` TF32 MMAs
+        # tensor work actually issued: per evaluation 2 (forward) + 2 (adjoint: the two Hessian-vector products; the
+        # forward activations come back from the tape) products of 128 x h x h MACs per 128-instance tile, each as
+        # `split` TF32 MMAs
         tiles = (B + 127) // 128
-        mma_flops = tiles * iters * H * S * (2 + 4) * split * 2.0 * 128 * h * h
+        mma_flops = tiles * iters * H * S * (2 + 2) * split * 2.0 * 128 * h * h
+        # HBM side of the same kernel: the activation tape (a1, a2, g1: 3 h floats per instance and evaluation) is
+        # written by the forward sweep and read back by the adjoint
+        tape_bytes = tiles * iters * H * S * 2.0 * 3 * h * 128 * 4
+        hbm_peak = peaks.get("hbm_gbs", 6500.0) if peaks else 6500.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
                     "frac": achieved / bf16_peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, this pool)" if peaks else
@@ -353,8 +361,13 @@ def main():
                     "tensor_pipe_frac": mma_flops / (kernel_ms * 1e-3) / 1e12 / tf32_peak,
                     "executed_over_algorithmic": mma_flops / algo,
                     "fp32_fma_peak_tflops": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak,
-                    "note": "FP32-level accuracy on TF32 tensor cores costs 3 MMAs per product at half the bf16 rate, and the "
-                            "adjoint recomputes activations (1.5x): frac vs the bf16 peak is bounded by 1/(6*1.5)=0.11"}
+                    "hbm": {"algorithmic_tape_bytes_per_launch": tape_bytes,
+                            "achieved_gbps": tape_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbps": hbm_peak,
+                            "frac": tape_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                            "measured_dram_bytes_per_launch": traffic},
+                    "note": "FP32-level accuracy on TF32 tensor cores costs 3 MMAs per product at half the bf16 rate: "
+                            "frac vs the bf16 peak is bounded by 1/6=0.17; the adjoint reads the forward activations "
+                            "from an HBM tape instead of recomputing them (4 tensor products per pair instead of 6)"}
     else:
         roofline = {"bound": "fp32-fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak, "traffic": traffic,

@@ -135,26 +135,28 @@ static void fill_tc_big(const phnn_model_desc* d, std::vector<unsigned char>& ou
                 }
 }
 
-// recA[k] = {W1[k][0..3], b1, b2, w3, br1}, recB[k] = Wr1[k][0..3], recC[k] = 10 symmetrised R_net
-// output weights + 2 pad
+// pair-interleaved records of the small layers (layout in TcShape): every field is {unit 2P, unit 2P+1}
 static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
     const int h = d->h, n = d->n;   // n == 4 for every tcgen05 shape
     const bool has_r = d->kind == PHNN_KIND_PHNN;
-    s.assign((size_t)h * (has_r ? 8 + 4 + 12 : 8), 0.f);
+    constexpr int RA = 20, RB = 8, RCP = 20;
+    s.assign((size_t)(h / 2) * (has_r ? RA + RB + RCP : RA), 0.f);
     float* rA = s.data();
-    float* rB = rA + (size_t)h * 8;
-    float* rC = rB + (size_t)h * 4;
+    float* rB = rA + (size_t)(h / 2) * RA;
+    float* rC = rB + (size_t)(h / 2) * RB;
     for (int k = 0; k < h; ++k) {
-        for (int i = 0; i < n; ++i) rA[k * 8 + i] = d->W1[k * n + i];
-        rA[k * 8 + 4] = d->b1[k];
-        rA[k * 8 + 5] = d->b2[k];
-        rA[k * 8 + 6] = d->W3[k];
+        const int P = k >> 1, o = k & 1;
+        for (int i = 0; i < n; ++i) rA[P * RA + 2 * i + o] = d->W1[k * n + i];
+        rA[P * RA + 8 + o] = d->b1[k];
+        rA[P * RA + 12 + o] = d->b2[k];
+        rA[P * RA + 14 + o] = d->W3[k];
+        rA[P * RA + 16 + o] = -2.f * d->W3[k];
         if (!has_r) continue;
-        rA[k * 8 + 7] = d->br1[k];
-        for (int i = 0; i < n; ++i) rB[k * 4 + i] = d->Wr1[k * n + i];
+        rA[P * RA + 10 + o] = d->br1[k];
+        for (int i = 0; i < n; ++i) rB[P * RB + 2 * i + o] = d->Wr1[k * n + i];
         for (int a = 0; a < n; ++a)
             for (int b = a; b < n; ++b)
-                rC[k * 12 + sym_idx(a, b)] = 0.5f * (d->Wr2[(size_t)(a * n + b) * h + k] + d->Wr2[(size_t)(b * n + a) * h + k]);
+                rC[P * RCP + 2 * sym_idx(a, b) + o] = 0.5f * (d->Wr2[(size_t)(a * n + b) * h + k] + d->Wr2[(size_t)(b * n + a) * h + k]);
     }
 }
 

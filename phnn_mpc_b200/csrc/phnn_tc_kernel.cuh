@@ -50,23 +50,29 @@ struct TcShape {
     static constexpr int B_TILE = HID * 128;  // bytes of one B K-block (hi or lo)
     static constexpr int NBE = 3;             // B ring entries
     static constexpr int TMEM_COLS = (2 * HID <= 32) ? 32 : (2 * HID <= 64) ? 64 : (2 * HID <= 128) ? 128 : (2 * HID <= 256) ? 256 : 512;
-    // small weights (floats): recA[k] = {W1[k][0..3], b1, b2, w3, br1}, recB[k] = Wr1[k][0..3],
-    // recC[k] = the 10 symmetrised R_net output weights (Wr2[ab][k] + Wr2[ba][k])/2, a <= b, + 2 pad
-    static constexpr int NSYM = 10, RC = 12;
+    // small weights (floats), interleaved by pairs of adjacent hidden units (P = units 2P, 2P+1; every field is
+    // the pair {unit 2P, unit 2P+1}) so that the element code runs on packed FP32 pairs (FFMA2):
+    //   recA[P] (20): {W1[.][0]} {W1[.][1]} | {W1[.][2]} {W1[.][3]} | {b1} {br1} | {b2} {w3} | {-2 w3} {0}
+    //   recB[P] (8):  {Wr1[.][0]} {Wr1[.][1]} | {Wr1[.][2]} {Wr1[.][3]}
+    //   recC[P] (20): the 10 symmetrised R_net output weights (Wr2[ab][.] + Wr2[ba][.])/2, a <= b
+    static constexpr int NSYM = 10, RA = 20, RB = 8, RCP = 20;
     static constexpr int O_RA = 0;
-    static constexpr int O_RB = O_RA + HID * 8;
-    static constexpr int O_RC = O_RB + (HAS_R ? HID * 4 : 0);
-    static constexpr int SMALL = O_RC + (HAS_R ? HID * RC : 0);
+    static constexpr int O_RB = O_RA + (HID / 2) * RA;
+    static constexpr int O_RC = O_RB + (HAS_R ? (HID / 2) * RB : 0);
+    static constexpr int SMALL = O_RC + (HAS_R ? (HID / 2) * RCP : 0);
     static constexpr int XW = 12 + 1 + NS;    // floats per thread in the pair exchange (S partial, H, dH)
     // shared memory map (bytes)
-    static constexpr int OFF_A = 1024;                        // 2 slots x (hi, lo)
-    static constexpr int OFF_B = OFF_A + 4 * A_TILE;          // NBE entries
+    static constexpr int NAS = 2;                             // A ring slots (a third slot measured no faster)
+    static constexpr int OFF_A = 1024;                        // NAS slots x (hi, lo)
+    static constexpr int OFF_B = OFF_A + NAS * 2 * A_TILE;    // NBE entries
     static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE;
     static constexpr int OFF_XCH = OFF_SMALL + SMALL * 4;
     static constexpr int SMEM_BYTES = OFF_XCH + XW * 256 * 4;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     // barrier indices
-    static constexpr int B_AFULL = 0, B_AEMPTY = 2, B_BFULL = 4, B_BEMPTY = 4 + NBE, B_ACC = 4 + 2 * NBE, B_SMALL = B_ACC + 2;
+    static constexpr int B_AFULL = 0, B_AEMPTY = NAS, B_BFULL = 2 * NAS, B_BEMPTY = 2 * NAS + NBE, B_ACC = 2 * NAS + 2 * NBE,
+                         B_SMALL = B_ACC + 2;
+    static_assert((B_SMALL + 1) * 8 <= 128, "barriers live in the first 128 bytes");
     static constexpr int THREADS = 320;
 };
 
@@ -155,12 +161,48 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
     while (!mbar_try(bar, parity)) __nanosleep(ns);
 }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float dot4(const float4& w, const float (&x)[4], float b) {
-    return fmaf(w.w, x[3], fmaf(w.z, x[2], fmaf(w.y, x[1], fmaf(w.x, x[0], b))));
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+// packed FP32 pairs: fma/mul/add/sub.rn.f32x2 (SASS FFMA2 / FMUL2 / FADD2; a broadcast scalar or a negated pair
+// is an operand modifier, and ptxas contracts 1 - a*a into one FFMA2)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+#define PHNN_F32X2_BINOP(name, op)                                                                                   \
+    __device__ __forceinline__ float2 name(float2 a, float2 b) {                                                     \
+        float2 d;                                                                                                    \
+        asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t" op                   \
+            ".rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"                                                    \
+            : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                        \
+        return d;                                                                                                    \
+    }
+PHNN_F32X2_BINOP(mul2, "mul")
+PHNN_F32X2_BINOP(add2, "add")
+PHNN_F32X2_BINOP(sub2, "sub")
+#undef PHNN_F32X2_BINOP
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 xy(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 zw(const float4& v) { return make_float2(v.z, v.w); }
+// tanh_tc on a pair (same operations per element)
+__device__ __forceinline__ float2 tanh_tc2(float2 x) {
+#ifdef PHNN_TC_TANH_LIBM
+    return make_float2(tanhf(x.x), tanhf(x.y));
+#else
+    const float2 t = mul2(x, bc2(2.8853900817779268f));
+    const float2 d = add2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), bc2(1.0f));
+    const float2 big = fma2(bc2(-2.0f), make_float2(rcp_approx(d.x), rcp_approx(d.y)), bc2(1.0f));
+    const float2 sm = mul2(x, fma2(mul2(x, x), bc2(-0.33333334f), bc2(1.0f)));
+    return make_float2(fabsf(x.x) < 0.04f ? sm.x : big.x, fabsf(x.y) < 0.04f ? sm.y : big.y);
+#endif
 }
 
 #ifdef PHNN_TC_PROFILE
-#define TCP_MARK(c, i) do { long long t_ = clock64(); (c).prof[i] += t_ - (c).tlast; (c).tlast = t_; } while (0)
+// per-phase cycle counters of threads 0 and 255, kept in shared memory so that the instrumented build keeps the
+// register allocation (and therefore the timing) of the production build
+#define TCP_MARK(c, i) do { const unsigned t_ = (unsigned)clock(); if ((c).prof) (c).prof[i] += (unsigned long long)(t_ - (c).tlast); (c).tlast = t_; } while (0)
 #else
 #define TCP_MARK(c, i) do { } while (0)
 #endif
@@ -174,6 +216,17 @@ __device__ __forceinline__ float dot4(const float4& w, const float (&x)[4], floa
 #endif
 #ifndef PHNN_TC_FENCE_EVERY
 #define PHNN_TC_FENCE_EVERY 4
+#endif
+// balance of the R_net work between the loops that feed the tensor pipe (units per K-block, of a thread's 16):
+// forward units done in the a1 loop (the rest in the a2 loop), backward units done in the da1 loop (the rest in the e2 loop)
+#ifndef PHNN_TC_RF_A
+#define PHNN_TC_RF_A 8
+#endif
+#ifndef PHNN_TC_RB_A
+#define PHNN_TC_RB_A 8
+#endif
+#ifndef PHNN_TC_RFENCE
+#define PHNN_TC_RFENCE 4
 #endif
 
 template <class SH> struct TcCtx;
@@ -200,11 +253,8 @@ struct TcCtx {
                      // float4 (a warp's 32 rows read/write 512 contiguous bytes); nullptr when no adjoint follows
     bool store;
 #ifdef PHNN_TC_PROFILE
-    long long prof[16];
-    long long tlast;
-    long long await[8];  // a_begin wait cycles per producing phase
-    long long sub[4];    // a_end: fences | syncwarp+arrive ; tmem wait
-    int aphase;
+    unsigned long long* prof;  // shared-memory counters of this thread (threads 0 and 255), else nullptr
+    unsigned tlast;
 #endif
 
     __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(phnn_smem); }
@@ -214,15 +264,8 @@ struct TcCtx {
 
     // ---- A-operand ring (element threads are the producers) ----
     __device__ __forceinline__ int a_begin() {
-        const int slot = ablk & 1;
-#ifdef PHNN_TC_PROFILE
-        const long long t0 = clock64();
-#endif
-        mbar_wait(&bars()[SH::B_AEMPTY + slot], ((ablk >> 1) & 1u) ^ 1u);
-#ifdef PHNN_TC_PROFILE
-        const long long t1 = clock64();
-        await[aphase] += t1 - t0;
-#endif
+        const int slot = ablk % SH::NAS;
+        mbar_wait(&bars()[SH::B_AEMPTY + slot], ((ablk / SH::NAS) & 1u) ^ 1u);
         return slot;
     }
     // four consecutive hidden units (chunk q of this thread's 16) of the current K-block
@@ -232,32 +275,19 @@ struct TcCtx {
         unsigned char* hi = phnn_smem + SH::OFF_A + (slot * 2) * SH::A_TILE + off;
         float4 h = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
         *reinterpret_cast<float4*>(hi) = h;
-        if (split == 3)
-            *reinterpret_cast<float4*>(hi + SH::A_TILE) = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+        if (split == 3) {
+            const float2 l01 = sub2(make_float2(v[0], v[1]), xy(h)), l23 = sub2(make_float2(v[2], v[3]), zw(h));
+            *reinterpret_cast<float4*>(hi + SH::A_TILE) = make_float4(l01.x, l01.y, l23.x, l23.y);
+        }
     }
     __device__ __forceinline__ void a_end(int slot) {
-#ifdef PHNN_TC_PROFILE
-        const long long t0 = clock64();
-#endif
         tc_fence_before();                                            // earlier tcgen05.ld of this thread are ordered first
 #ifndef PHNN_TC_EXP_NOFENCE  // timing experiment (unsafe): cost of the MEMBAR.ALL.CTA the proxy fence lowers to
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
 #endif
-#ifdef PHNN_TC_PROFILE
-        const long long t1 = clock64();
-#endif
-#ifdef PHNN_TC_ARRIVE_ALL
-        mbar_arrive(&bars()[SH::B_AFULL + slot]);
-#else
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars()[SH::B_AFULL + slot]);
-#endif
         ++ablk;
-#ifdef PHNN_TC_PROFILE
-        const long long t2 = clock64();
-        sub[0] += t1 - t0;
-        sub[1] += t2 - t1;
-#endif
     }
     // wait for the next product's accumulator; returns its TMEM address for this thread's lane quadrant
     __device__ __forceinline__ uint32_t acc_wait() {
@@ -271,9 +301,11 @@ struct TcCtx {
     __device__ __forceinline__ float4* tape4(int which, int jb, int q) const {
         return reinterpret_cast<float4*>(tape) + ((size_t)ev * 3 + which) * TAPE_ARR4 + ((jb * 2 + hf) * 4 + q) * 128 + row;
     }
+    // LAST: the final use of these lines (evict-first), otherwise they are read once more soon
+    template <bool LAST>
     __device__ __forceinline__ void tape_load(int which, int jb, float4 (&v)[4]) const {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = __ldcg(tape4(which, jb, q));
+        for (int q = 0; q < 4; ++q) v[q] = LAST ? __ldcs(tape4(which, jb, q)) : __ldcg(tape4(which, jb, q));
     }
     // pair exchange: returns mine + partner's for n values starting at slot s0
     template <int N>
@@ -312,22 +344,66 @@ __device__ __forceinline__ void tc_make_S(const KParams& p, const float* Sp, flo
 #pragma unroll
         for (int b = 0; b < 4; ++b) S[a][b] = Sp[sym_idx(a, b)] + p.bsym[sym_idx(a, b)];
 }
-// accumulate r * recC[k] into the 10 packed S sums
-__device__ __forceinline__ void tc_acc_S(const float* rC, int k, float r, float* Sp) {
-    const float4 c0 = lds4(rC + k * 12), c1 = lds4(rC + k * 12 + 4);
-    const float2 c2 = *reinterpret_cast<const float2*>(rC + k * 12 + 8);
-    Sp[0] = fmaf(c0.x, r, Sp[0]); Sp[1] = fmaf(c0.y, r, Sp[1]); Sp[2] = fmaf(c0.z, r, Sp[2]); Sp[3] = fmaf(c0.w, r, Sp[3]);
-    Sp[4] = fmaf(c1.x, r, Sp[4]); Sp[5] = fmaf(c1.y, r, Sp[5]); Sp[6] = fmaf(c1.z, r, Sp[6]); Sp[7] = fmaf(c1.w, r, Sp[7]);
-    Sp[8] = fmaf(c2.x, r, Sp[8]); Sp[9] = fmaf(c2.y, r, Sp[9]);
-}
 
-// phase A of the forward evaluation: a1 = tanh(W1 y + b1) -> A ring (product z2 = W2 a1) and the tape,
-// and the R_net hidden layer with its symmetrised output sums
+// ---- element arithmetic on pairs of adjacent hidden units (FFMA2 / FMUL2 / FADD2) -------------------------
+// The small-layer records are interleaved by pairs (TcShape), so the two units of a pair share every
+// instruction: W1 x + b is four FFMA2 for two units, an accumulation over hidden units keeps an (even, odd)
+// pair of partial sums that is folded once at the end.
+
+// pre-activations of the pair: b + sum_i W[.][i] x_i ; w01 = {W[.][0] pair, W[.][1] pair}, w23 likewise
+__device__ __forceinline__ float2 pair_affine(const float4& w01, const float4& w23, const float (&x)[4], float2 b) {
+    float2 s = fma2(xy(w01), bc2(x[0]), b);
+    s = fma2(zw(w01), bc2(x[1]), s);
+    s = fma2(xy(w23), bc2(x[2]), s);
+    return fma2(zw(w23), bc2(x[3]), s);
+}
+__device__ __forceinline__ float2 pair_linear(const float4& w01, const float4& w23, const float (&x)[4]) {
+    float2 s = mul2(xy(w01), bc2(x[0]));
+    s = fma2(zw(w01), bc2(x[1]), s);
+    s = fma2(xy(w23), bc2(x[2]), s);
+    return fma2(zw(w23), bc2(x[3]), s);
+}
+// acc[i] += W[.][i] pair * t pair  (the transposed product W^T t over hidden units, (even, odd) partial sums)
+__device__ __forceinline__ void pair_scatter(const float4& w01, const float4& w23, float2 t, float2 (&acc)[4]) {
+    acc[0] = fma2(xy(w01), t, acc[0]);
+    acc[1] = fma2(zw(w01), t, acc[1]);
+    acc[2] = fma2(xy(w23), t, acc[2]);
+    acc[3] = fma2(zw(w23), t, acc[3]);
+}
+__device__ __forceinline__ float2 one_minus_sq(float2 a) { return sub2(bc2(1.f), mul2(a, a)); }  // one FFMA2
+
+// pair index of (K-block kb, this thread's i-th pair of 8)
 template <class SH>
-__device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], const float (&y)[4], float* Sp) {
+__device__ __forceinline__ int tc_pair(const TcCtx<SH>& c, int kb, int i) { return kb * 16 + c.hf * 8 + i; }
+
+// R_net hidden layer and symmetrised output sums for pairs [I0, I1) of this thread's 8 in K-block kb
+template <int I0, int I1, class SH>
+__device__ __forceinline__ void tc_rfwd_pairs(const TcCtx<SH>& c, int kb, const float (&y)[4], float2 (&Sp2)[10]) {
     const float* rA = c.small() + SH::O_RA;
     const float* rB = c.small() + SH::O_RB;
     const float* rC = c.small() + SH::O_RC;
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+        const int P = tc_pair(c, kb, i);
+        const float* rb = rB + P * SH::RB;
+        const float2 r = tanh_tc2(pair_affine(lds4(rb), lds4(rb + 4), y, lds2(rA + P * SH::RA + 10)));
+        const float* rc = rC + P * SH::RCP;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 cc = lds4(rc + 4 * j);
+            Sp2[2 * j] = fma2(xy(cc), r, Sp2[2 * j]);
+            Sp2[2 * j + 1] = fma2(zw(cc), r, Sp2[2 * j + 1]);
+        }
+        if ((i - I0) % PHNN_TC_RFENCE == PHNN_TC_RFENCE - 1) sched_fence();
+    }
+}
+
+// phase A of the forward evaluation: a1 = tanh(W1 y + b1) -> A ring (product z2 = W2 a1) and the tape,
+// and part of the R_net hidden layer with its symmetrised output sums.  The R_net pairs of a K-block run after
+// the block's hand-off, so the MMA starts as early as possible and the last block's tail is covered.
+template <class SH>
+__device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], const float (&y)[4], float2 (&Sp2)[10]) {
+    const float* rA = c.small() + SH::O_RA;
 #pragma unroll 1
     for (int kb = 0; kb < SH::NKB; ++kb) {
         const int slot = c.a_begin();
@@ -335,20 +411,16 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
         for (int q = 0; q < 4; ++q) {
             float av[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = kb * 32 + c.hf * 16 + q * 4 + e;
-                const float4 w1 = lds4(rA + k * 8), m = lds4(rA + k * 8 + 4);
-                av[e] = tanh_tc(dot4(w1, z, m.x));
-                if constexpr (SH::HAS_R) {
-                    const float r = tanh_tc(dot4(lds4(rB + k * 4), y, m.w));
-                    tc_acc_S(rC, k, r, Sp);
-                }
+            for (int e = 0; e < 2; ++e) {
+                const float* r = rA + tc_pair(c, kb, q * 2 + e) * SH::RA;
+                const float2 a = tanh_tc2(pair_affine(lds4(r), lds4(r + 4), z, lds2(r + 8)));
+                av[2 * e] = a.x; av[2 * e + 1] = a.y;
             }
-            if (c.tape) *c.tape4(1, kb, q) = make_float4(av[0], av[1], av[2], av[3]);
+            if (c.tape) *c.tape4(1, kb, q) = make_float4(av[0], av[1], av[2], av[3]);  // read back in phase C
             c.a_put4(slot, q, av);
-            if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
         }
         c.a_end(slot);
+        if constexpr (SH::HAS_R) tc_rfwd_pairs<0, PHNN_TC_RF_A / 2>(c, kb, y, Sp2);
     }
 }
 
@@ -372,12 +444,10 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
     constexpr int NKB = SH::NKB;
     const float* rA = c.small() + SH::O_RA;
     float X[SH::XW];  // [0,10) S sums, [12] H partial, [13,17) dH partial
+    float2 Sp2[10];
 #pragma unroll
-    for (int i = 0; i < SH::XW; ++i) X[i] = 0.f;
+    for (int i = 0; i < 10; ++i) Sp2[i] = make_float2(0.f, 0.f);
     TCP_MARK(c, 15);
-#ifdef PHNN_TC_PROFILE
-    c.aphase = 0;
-#endif
     float z[4];
     Canon cq = {};
     if constexpr (SH::MK == MK_CANON) {
@@ -389,65 +459,89 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) z[i] = y[i];
     }
-    tc_phase_a1(c, z, y, X);
-#ifdef PHNN_TC_PROFILE
-    c.aphase = 1;
-#endif
+    tc_phase_a1(c, z, y, Sp2);
     TCP_MARK(c, 0);
     // ---- phase B: a2, H, delta2 -> product 2 (g1 = W2^T delta2) ----
     {
         const uint32_t tacc = c.acc_wait();
         TCP_MARK(c, 1);
-        float Hp = 0.f;
+        float2 Hp2 = make_float2(0.f, 0.f);
         for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&zr)[16]) {
             const int slot = c.a_begin();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float dv[4], a2v[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = jb * 32 + c.hf * 16 + q * 4 + e;
-                    const float4 m = lds4(rA + j * 8 + 4);
-                    const float a2 = tanh_tc(__uint_as_float(zr[q * 4 + e]) + m.y);
-                    a2v[e] = a2;
-                    Hp = fmaf(m.z, a2, Hp);
-                    dv[e] = fmaf(-a2, a2, 1.f) * m.z;
+                for (int e = 0; e < 2; ++e) {
+                    const float4 m = lds4(rA + tc_pair(c, jb, q * 2 + e) * SH::RA + 12);  // {b2 pair, w3 pair}
+                    const float2 zz = make_float2(__uint_as_float(zr[q * 4 + 2 * e]), __uint_as_float(zr[q * 4 + 2 * e + 1]));
+                    const float2 a2 = tanh_tc2(add2(zz, xy(m)));
+                    Hp2 = fma2(zw(m), a2, Hp2);
+                    const float2 d = mul2(one_minus_sq(a2), zw(m));
+                    a2v[2 * e] = a2.x; a2v[2 * e + 1] = a2.y;
+                    dv[2 * e] = d.x; dv[2 * e + 1] = d.y;
                 }
-                if (c.tape) *c.tape4(0, jb, q) = make_float4(a2v[0], a2v[1], a2v[2], a2v[3]);
+                if (c.tape) __stcs(c.tape4(0, jb, q), make_float4(a2v[0], a2v[1], a2v[2], a2v[3]));
                 c.a_put4(slot, q, dv);
                 if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
             }
             c.a_end(slot);
+            // the rest of the R_net forward pairs rides here: this loop otherwise waits for the MMA
+            if constexpr (SH::HAS_R) tc_rfwd_pairs<PHNN_TC_RF_A / 2, 8>(c, jb, y, Sp2);
         });
-        X[12] = Hp;
+        X[12] = Hp2.x + Hp2.y;
     }
     TCP_MARK(c, 2);
     // ---- phase C: dH = W1^T (s1 * g1) ----
     {
         const uint32_t tacc = c.acc_wait();
         TCP_MARK(c, 3);
-        float g0 = 0.f, g1s = 0.f, g2 = 0.f, g3 = 0.f;
-        for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
-            if (c.tape) {
+        float2 G2[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *c.tape4(2, kb, q) = make_float4(__uint_as_float(gr[q * 4]), __uint_as_float(gr[q * 4 + 1]),
-                                                     __uint_as_float(gr[q * 4 + 2]), __uint_as_float(gr[q * 4 + 3]));
-            }
+        for (int i = 0; i < 4; ++i) G2[i] = make_float2(0.f, 0.f);
+        if (c.tape) {
+            // a1 comes back from the tape (written by this thread in phase A, still in L2)
+            float4 an[4];
+            c.tape_load<false>(1, 0, an);
+            for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
+                float4 ac[4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = kb * 32 + c.hf * 16 + i;
-                const float4 w1 = lds4(rA + k * 8);
-                const float a1 = tanh_tc(dot4(w1, z, rA[k * 8 + 4]));
-                if ((i & 3) == 3) sched_fence();
-                const float d1 = fmaf(-a1, a1, 1.f) * __uint_as_float(gr[i]);
-                g0 = fmaf(w1.x, d1, g0); g1s = fmaf(w1.y, d1, g1s); g2 = fmaf(w1.z, d1, g2); g3 = fmaf(w1.w, d1, g3);
-            }
-        });
-        X[13] = g0; X[14] = g1s; X[15] = g2; X[16] = g3;
+                for (int q = 0; q < 4; ++q) ac[q] = an[q];
+                if (kb + 1 < NKB) c.tape_load<false>(1, kb + 1, an);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    __stcs(c.tape4(2, kb, q), make_float4(__uint_as_float(gr[q * 4]), __uint_as_float(gr[q * 4 + 1]),
+                                                          __uint_as_float(gr[q * 4 + 2]), __uint_as_float(gr[q * 4 + 3])));
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float* r = rA + tc_pair(c, kb, q * 2 + e) * SH::RA;
+                        const float2 a1 = e ? zw(ac[q]) : xy(ac[q]);
+                        const float2 g = make_float2(__uint_as_float(gr[q * 4 + 2 * e]), __uint_as_float(gr[q * 4 + 2 * e + 1]));
+                        pair_scatter(lds4(r), lds4(r + 4), mul2(one_minus_sq(a1), g), G2);
+                    }
+                }
+            });
+        } else {
+            for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float* r = rA + tc_pair(c, kb, i) * SH::RA;
+                    const float4 w01 = lds4(r), w23 = lds4(r + 4);
+                    const float2 a1 = tanh_tc2(pair_affine(w01, w23, z, lds2(r + 8)));
+                    if ((i & 1) == 1) sched_fence();
+                    const float2 g = make_float2(__uint_as_float(gr[2 * i]), __uint_as_float(gr[2 * i + 1]));
+                    pair_scatter(w01, w23, mul2(one_minus_sq(a1), g), G2);
+                }
+            });
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) X[13 + i] = G2[i].x + G2[i].y;
         tc_fence_before();
     }
     TCP_MARK(c, 4);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) X[i] = Sp2[i].x + Sp2[i].y;
+    X[10] = 0.f; X[11] = 0.f;
     c.exchange(X);
     TCP_MARK(c, 5);
     if (c.tape && c.store) {
@@ -490,22 +584,27 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
 // at the same stage state and the Hessian-vector product of H_net.
 // Products: dz2 = W2 da1 -> acc0, dg1 = W2^T e2 -> acc1.
 // ---------------------------------------------------------------------------------------
-// R_net backward chain for one hidden unit: xbar += Wr1[k]^T (1 - r^2) (Wr2sym[k] . Rb)
+// R_net backward chain for one pair of hidden units: xbar += Wr1[k]^T (1 - r^2) (Wr2sym[k] . Rb)
 template <class SH>
-__device__ __forceinline__ void tc_rback_unit(const TcCtx<SH>& c, int k, const float (&y)[4], const float (&Rb)[12], float (&X4)[4]) {
+__device__ __forceinline__ void tc_rback_pair(const TcCtx<SH>& c, int P, const float (&y)[4], const float (&Rb)[12], float2 (&X2)[4]) {
     const float* rA = c.small() + SH::O_RA;
     const float* rB = c.small() + SH::O_RB;
-    const float* rC = c.small() + SH::O_RC;
-    const float4 c0 = lds4(rC + k * 12), c1 = lds4(rC + k * 12 + 4);
-    const float2 c2 = *reinterpret_cast<const float2*>(rC + k * 12 + 8);
-    float rb = c0.x * Rb[0];
-    rb = fmaf(c0.y, Rb[1], rb); rb = fmaf(c0.z, Rb[2], rb); rb = fmaf(c0.w, Rb[3], rb);
-    rb = fmaf(c1.x, Rb[4], rb); rb = fmaf(c1.y, Rb[5], rb); rb = fmaf(c1.z, Rb[6], rb); rb = fmaf(c1.w, Rb[7], rb);
-    rb = fmaf(c2.x, Rb[8], rb); rb = fmaf(c2.y, Rb[9], rb);
-    const float4 wr = lds4(rB + k * 4);
-    const float r1 = tanh_tc(dot4(wr, y, rA[k * 8 + 7]));
-    const float zb = rb * fmaf(-r1, r1, 1.f);
-    X4[0] = fmaf(wr.x, zb, X4[0]); X4[1] = fmaf(wr.y, zb, X4[1]); X4[2] = fmaf(wr.z, zb, X4[2]); X4[3] = fmaf(wr.w, zb, X4[3]);
+    const float* rc = c.small() + SH::O_RC + P * SH::RCP;
+    float2 rb;
+    {
+        const float4 cc = lds4(rc);
+        rb = fma2(zw(cc), bc2(Rb[1]), mul2(xy(cc), bc2(Rb[0])));
+    }
+#pragma unroll
+    for (int j = 1; j < 5; ++j) {
+        const float4 cc = lds4(rc + 4 * j);
+        rb = fma2(xy(cc), bc2(Rb[2 * j]), rb);
+        rb = fma2(zw(cc), bc2(Rb[2 * j + 1]), rb);
+    }
+    const float* rbw = rB + P * SH::RB;
+    const float4 u01 = lds4(rbw), u23 = lds4(rbw + 4);
+    const float2 r1 = tanh_tc2(pair_affine(u01, u23, y, lds2(rA + P * SH::RA + 10)));
+    pair_scatter(u01, u23, mul2(rb, one_minus_sq(r1)), X2);
 }
 
 template <class SH>
@@ -514,9 +613,6 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     constexpr int NKB = SH::NKB;
     const float* rA = c.small() + SH::O_RA;
     TCP_MARK(c, 15);
-#ifdef PHNN_TC_PROFILE
-    c.aphase = 2;
-#endif
     float z[4], w[4], G4[4], sv[4], Rb[12];
     Canon cq = {};
     float pb[2] = {0.f, 0.f}, pdb[2] = {0.f, 0.f};
@@ -569,79 +665,100 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
                 Rb[sym_idx(a, b)] = (a == b ? -0.5f : -1.0f) * (v[a] * tg[b] + G4[a] * sv[b] + v[b] * tg[a] + G4[b] * sv[a]);
         Rb[10] = 0.f; Rb[11] = 0.f;
     }
-    float X4[4] = {0.f, 0.f, 0.f, 0.f};  // xbar partial over my hidden units
-    // ---- A3: da1 = s1 * (W1 w) -> product 1 (dz2 = W2 da1), with the g1 half of xbar_H (sdot1 * g1) and the
-    //      first half of the R_net chain in the same loop (the loop runs at the pace of the MMA) ----
+    // xbar partials over my hidden units as (even, odd) pairs: X2 from the R_net chain and the dg1 half of
+    // xbar_H, T2 the g1 half of xbar_H without its factor -2
+    float2 X2[4], T2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { X2[i] = make_float2(0.f, 0.f); T2[i] = make_float2(0.f, 0.f); }
+    // ---- A3: da1 = s1 * (W1 w) -> product 1 (dz2 = W2 da1), with the g1 half of xbar_H (sdot1 * g1) and part
+    //      of the R_net chain in the same loop (the loop runs at the pace of the MMA) ----
     {
         float4 an[4], gn[4];
-        c.tape_load(1, 0, an);
-        c.tape_load(2, 0, gn);
+        c.tape_load<false>(1, 0, an);
+        c.tape_load<true>(2, 0, gn);
 #pragma unroll 1
         for (int kb = 0; kb < NKB; ++kb) {
             float4 ac[4], gc[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) { ac[q] = an[q]; gc[q] = gn[q]; }
+#ifndef PHNN_TC_LOAD_AFTER
             if (kb + 1 < NKB) {
-                c.tape_load(1, kb + 1, an);
-                c.tape_load(2, kb + 1, gn);
+                c.tape_load<false>(1, kb + 1, an);
+                c.tape_load<true>(2, kb + 1, gn);
             }
+#endif
             const int slot = c.a_begin();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
-                const float g1v[4] = {gc[q].x, gc[q].y, gc[q].z, gc[q].w};
                 float av[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = kb * 32 + c.hf * 16 + q * 4 + e;
-                    const float4 w1 = lds4(rA + k * 8);
-                    const float a1 = a1v[e];
-                    av[e] = fmaf(-a1, a1, 1.f) * dot4(w1, w, 0.f);
-                    const float t = -2.f * a1 * av[e] * g1v[e];
-                    X4[0] = fmaf(w1.x, t, X4[0]); X4[1] = fmaf(w1.y, t, X4[1]); X4[2] = fmaf(w1.z, t, X4[2]); X4[3] = fmaf(w1.w, t, X4[3]);
+                for (int e = 0; e < 2; ++e) {
+                    const float* r = rA + tc_pair(c, kb, q * 2 + e) * SH::RA;
+                    const float4 w01 = lds4(r), w23 = lds4(r + 4);
+                    const float2 a1 = e ? zw(ac[q]) : xy(ac[q]);
+                    const float2 g1 = e ? zw(gc[q]) : xy(gc[q]);
+                    const float2 da = mul2(one_minus_sq(a1), pair_linear(w01, w23, w));
+                    pair_scatter(w01, w23, mul2(mul2(a1, da), g1), T2);
+                    av[2 * e] = da.x; av[2 * e + 1] = da.y;
                 }
                 c.a_put4(slot, q, av);
             }
             c.a_end(slot);
+#ifdef PHNN_TC_LOAD_AFTER
+            // the next block's tape loads go out after the hand-off: the fence / release of a_end waits for
+            // every outstanding load of the thread, so loads issued before it are not a prefetch
+            if (kb + 1 < NKB) {
+                c.tape_load<false>(1, kb + 1, an);
+                c.tape_load<true>(2, kb + 1, gn);
+            }
+#endif
             if constexpr (SH::HAS_R) {
-#pragma unroll 4
-                for (int i = 0; i < 8; ++i) tc_rback_unit(c, kb * 32 + c.hf * 16 + i, y, Rb, X4);
+#pragma unroll
+                for (int i = 0; i < PHNN_TC_RB_A / 2; ++i) {
+                    tc_rback_pair(c, tc_pair(c, kb, i), y, Rb, X2);
+                    if (i % 2 == 1) sched_fence();
+                }
             }
         }
     }
     TCP_MARK(c, 6);
-#ifdef PHNN_TC_PROFILE
-    c.aphase = 5;
-#endif
-    // ---- B3: e2 = -2 a2 da2 w3 -> product 2 (dg1 = W2^T e2); second half of the R_net chain ----
+    // ---- B3: e2 = -2 a2 da2 w3 -> product 2 (dg1 = W2^T e2); the rest of the R_net chain ----
     {
         float4 an[4];
-        c.tape_load(0, 0, an);
+        c.tape_load<true>(0, 0, an);
         const uint32_t tacc = c.acc_wait();
         TCP_MARK(c, 7);
         for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&dz)[16]) {
             float4 a2q[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) a2q[q] = an[q];
-            if (jb + 1 < NKB) c.tape_load(0, jb + 1, an);
+#ifndef PHNN_TC_LOAD_AFTER
+            if (jb + 1 < NKB) c.tape_load<true>(0, jb + 1, an);
+#endif
             const int slot = c.a_begin();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float a2v[4] = {a2q[q].x, a2q[q].y, a2q[q].z, a2q[q].w};
                 float ev[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = jb * 32 + c.hf * 16 + q * 4 + e;
-                    const float w3 = rA[j * 8 + 6];
-                    const float da2 = fmaf(-a2v[e], a2v[e], 1.f) * __uint_as_float(dz[q * 4 + e]);
-                    ev[e] = -2.f * a2v[e] * da2 * w3;
+                for (int e = 0; e < 2; ++e) {
+                    const float2 m2w3 = lds2(rA + tc_pair(c, jb, q * 2 + e) * SH::RA + 16);  // -2 w3 pair
+                    const float2 a2 = e ? zw(a2q[q]) : xy(a2q[q]);
+                    const float2 dzz = make_float2(__uint_as_float(dz[q * 4 + 2 * e]), __uint_as_float(dz[q * 4 + 2 * e + 1]));
+                    const float2 ee = mul2(mul2(a2, mul2(one_minus_sq(a2), dzz)), m2w3);
+                    ev[2 * e] = ee.x; ev[2 * e + 1] = ee.y;
                 }
                 c.a_put4(slot, q, ev);
             }
             c.a_end(slot);
+#ifdef PHNN_TC_LOAD_AFTER
+            if (jb + 1 < NKB) c.tape_load<true>(0, jb + 1, an);
+#endif
             if constexpr (SH::HAS_R) {
-#pragma unroll 4
-                for (int i = 8; i < 16; ++i) tc_rback_unit(c, jb * 32 + c.hf * 16 + i, y, Rb, X4);
+#pragma unroll
+                for (int i = PHNN_TC_RB_A / 2; i < 8; ++i) {
+                    tc_rback_pair(c, tc_pair(c, jb, i), y, Rb, X2);
+                    if ((i - PHNN_TC_RB_A / 2) % 2 == 1) sched_fence();
+                }
             }
         });
     }
@@ -649,29 +766,31 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     // ---- C4: the dg1 half of xbar_H ----
     {
         float4 an[4];
-        c.tape_load(1, 0, an);
+        c.tape_load<true>(1, 0, an);
         const uint32_t tacc = c.acc_wait();
         TCP_MARK(c, 9);
         for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&dg)[16]) {
             float4 ac[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) ac[q] = an[q];
-            if (kb + 1 < NKB) c.tape_load(1, kb + 1, an);
+            if (kb + 1 < NKB) c.tape_load<true>(1, kb + 1, an);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float a1v[4] = {ac[q].x, ac[q].y, ac[q].z, ac[q].w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = kb * 32 + c.hf * 16 + q * 4 + e;
-                    const float4 w1 = lds4(rA + k * 8);
-                    const float t = fmaf(-a1v[e], a1v[e], 1.f) * __uint_as_float(dg[q * 4 + e]);
-                    X4[0] = fmaf(w1.x, t, X4[0]); X4[1] = fmaf(w1.y, t, X4[1]); X4[2] = fmaf(w1.z, t, X4[2]); X4[3] = fmaf(w1.w, t, X4[3]);
+                for (int e = 0; e < 2; ++e) {
+                    const float* r = rA + tc_pair(c, kb, q * 2 + e) * SH::RA;
+                    const float2 a1 = e ? zw(ac[q]) : xy(ac[q]);
+                    const float2 dgg = make_float2(__uint_as_float(dg[q * 4 + 2 * e]), __uint_as_float(dg[q * 4 + 2 * e + 1]));
+                    pair_scatter(lds4(r), lds4(r + 4), mul2(one_minus_sq(a1), dgg), X2);
                 }
             }
         });
         tc_fence_before();
     }
     TCP_MARK(c, 10);
+    float X4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) X4[i] = fmaf(-2.f, T2[i].x + T2[i].y, X2[i].x + X2[i].y);
     c.exchange(X4);
     TCP_MARK(c, 5);
     if constexpr (SH::MK == MK_CANON) {
@@ -779,15 +898,10 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-#ifdef PHNN_TC_ARRIVE_ALL
-        mbar_init(&bars[SH::B_AFULL + 0], 256);
-        mbar_init(&bars[SH::B_AFULL + 1], 256);
-#else
-        mbar_init(&bars[SH::B_AFULL + 0], 8);
-        mbar_init(&bars[SH::B_AFULL + 1], 8);
-#endif
-        mbar_init(&bars[SH::B_AEMPTY + 0], 1);
-        mbar_init(&bars[SH::B_AEMPTY + 1], 1);
+        for (int e = 0; e < SH::NAS; ++e) {
+            mbar_init(&bars[SH::B_AFULL + e], 8);
+            mbar_init(&bars[SH::B_AEMPTY + e], 1);
+        }
         for (int e = 0; e < SH::NBE; ++e) {
             mbar_init(&bars[SH::B_BFULL + e], 1);
             mbar_init(&bars[SH::B_BEMPTY + e], 1);
@@ -848,11 +962,10 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         c.ev = 0;
         mbar_wait(&bars[SH::B_SMALL], 0);
 #ifdef PHNN_TC_PROFILE
-        for (int i = 0; i < 16; ++i) c.prof[i] = 0;
-        for (int i = 0; i < 8; ++i) c.await[i] = 0;
-        for (int i = 0; i < 4; ++i) c.sub[i] = 0;
-        c.aphase = 0;
-        c.tlast = clock64();
+        c.prof = (threadIdx.x == 0 || threadIdx.x == 255) ? reinterpret_cast<unsigned long long*>(phnn_smem + 128) + (threadIdx.x ? 16 : 0) : nullptr;
+        if (c.prof)
+            for (int i = 0; i < 16; ++i) c.prof[i] = 0;
+        c.tlast = (unsigned)clock();
 #endif
         if (steal) {
             run_job(c, p, ss, c.row);
@@ -862,12 +975,8 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         }
         tc_fence_before();
 #ifdef PHNN_TC_PROFILE
-        if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 255) && p.dbg)
-        {
-            for (int i = 0; i < 16; ++i) p.dbg[(threadIdx.x ? 16 : 0) + i] = c.prof[i];
-            if (threadIdx.x == 0) for (int i = 0; i < 8; ++i) p.dbg[32 + i] = c.await[i];
-            if (threadIdx.x == 0) for (int i = 0; i < 4; ++i) p.dbg[40 + i] = c.sub[i];
-        }
+        if (blockIdx.x == 0 && c.prof && p.dbg)
+            for (int i = 0; i < 16; ++i) p.dbg[(threadIdx.x ? 16 : 0) + i] = (long long)c.prof[i];
 #endif
     } else if (warp == 8) {
         // ===== MMA issuer =====
@@ -875,6 +984,9 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         const uint32_t a_base = smem_u32(phnn_smem + SH::OFF_A), b_base = smem_u32(phnn_smem + SH::OFF_B);
         uint32_t ablk = 0, bent = 0;
         long long qtot = 0;  // products issued so far (accumulator / operand parity continues across units)
+#ifdef PHNN_TC_PROFILE
+        long long mma_wait_a = 0, mma_wait_b = 0;  // cycles the issuer waited for operand A (element threads) / B (weights)
+#endif
         for (long long unit = 0;; ++unit) {
             if (steal ? ss.grab() < 0 : unit >= my_tiles) break;
             if (lane == 0) {
@@ -883,11 +995,21 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                     const uint32_t acc = tbase + (uint32_t)(qtot & 1) * HID;
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
-                        const uint32_t slot = ablk & 1u;
-                        mbar_wait_sleep(&bars[SH::B_AFULL + slot], (ablk >> 1) & 1u, PHNN_TC_MMA_SLEEP);
+                        const uint32_t slot = ablk % SH::NAS;
+#ifdef PHNN_TC_PROFILE
+                        const long long t0 = clock64();
+#endif
+                        mbar_wait_sleep(&bars[SH::B_AFULL + slot], (ablk / SH::NAS) & 1u, PHNN_TC_MMA_SLEEP);
                         const uint32_t a_hi = a_base + (slot * 2) * SH::A_TILE, a_lo = a_hi + SH::A_TILE;
                         uint32_t e = bent % SH::NBE;
+#ifdef PHNN_TC_PROFILE
+                        const long long t1 = clock64();
+#endif
                         mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, PHNN_TC_MMA_SLEEP);
+#ifdef PHNN_TC_PROFILE
+                        mma_wait_a += t1 - t0;
+                        mma_wait_b += clock64() - t1;
+#endif
                         tc_fence_after();
                         uint32_t b_t = b_base + e * SH::B_TILE;
 #pragma unroll
@@ -902,7 +1024,13 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
                         ++bent;
                         if (split == 3) {
                             e = bent % SH::NBE;
+#ifdef PHNN_TC_PROFILE
+                            const long long t2 = clock64();
+#endif
                             mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, PHNN_TC_MMA_SLEEP);
+#ifdef PHNN_TC_PROFILE
+                            mma_wait_b += clock64() - t2;
+#endif
                             tc_fence_after();
                             b_t = b_base + e * SH::B_TILE;
 #pragma unroll
@@ -919,6 +1047,9 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
             }
             __syncwarp();
         }
+#ifdef PHNN_TC_PROFILE
+        if (blockIdx.x == 0 && lane == 0 && p.dbg) { p.dbg[32] = mma_wait_a; p.dbg[33] = mma_wait_b; }
+#endif
     } else {
         // ===== weight producer (TMA bulk copies of pre-swizzled K-blocks) =====
         if (lane == 0) {
@@ -932,22 +1063,29 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
             if (lane == 0) {
 #pragma unroll 1
                 for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
-                    if (tape && !(qq & 1)) {
-                        // adjoint evaluations run from the last taped evaluation down: while evaluation e is in
-                        // flight, pull the tape of e - 1 (written a whole sweep ago, so in HBM) into L2
-                        const long long qi = qq % per_iter - 2LL * nfwd;
-                        if (qi >= 0) {
-                            const long long e_next = (long long)E - 2 - (qi >> 1);
-                            if (e_next >= 0) {
-                                const char* src = reinterpret_cast<const char*>(tape + (size_t)e_next * tape_eval);
-                                for (int off = 0; off < (int)(tape_eval * 4); off += 65536)
-                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + off), "r"(65536) : "memory");
-                            }
-                        }
-                    }
+                    // adjoint products of evaluation e (descending): 0 -> da1 loop (reads a1, g1), 1 -> e2 loop (reads a2)
+                    const long long qi = tape ? qq % per_iter - 2LL * nfwd : -1;
                     const unsigned char* src = p.wtc + (size_t)(qtot & 1) * SH::NKB * 2 * SH::B_TILE;
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
+                        if (qi >= 0) {
+                            // pull the tape blocks the element threads will read PF_AHEAD K-block steps from now
+                            // into L2 (they were written a whole sweep ago, so they come from HBM)
+                            constexpr int PF_AHEAD = 3;
+                            int step = (int)(qi & 1) * SH::NKB + kb + PF_AHEAD;
+                            long long te = (long long)E - 1 - (qi >> 1);
+                            if (step >= 2 * SH::NKB) { step -= 2 * SH::NKB; --te; }
+                            if (te >= 0) {
+                                const float* ev0 = tape + (size_t)te * tape_eval;
+                                constexpr size_t ARR = (size_t)HID * 128, BLK = 4096;  // floats per array / per K-block
+                                if (step < SH::NKB) {
+                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ev0 + ARR + step * BLK), "r"(16384) : "memory");
+                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ev0 + 2 * ARR + step * BLK), "r"(16384) : "memory");
+                                } else {
+                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ev0 + (step - SH::NKB) * BLK), "r"(16384) : "memory");
+                                }
+                            }
+                        }
                         for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
                             const uint32_t e = bent % SH::NBE;
                             mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, PHNN_TC_PROD_SLEEP);

@@ -26,12 +26,10 @@ ms = e0.elapsed_time(e1)
 npair = iters * H * 4
 names = ["fwdA:a1+Rnet", "wait acc z2", "fwdB:a2,delta2", "wait acc g1", "fwdC:gradH", "exchanges", "adjA3:da1+xbar(g1)+R/2", "adj wait dz2",
          "adjB3:e2+R/2", "adj wait dg1", "adjC4", "-", "-", "-", "-", "outside evals"]
-aw = dbg.cpu().numpy()[32:40]
 d = dbg.cpu().numpy()[:32].reshape(2, 16)
 print("B=%d  %.2f ms  -> %.0f cycles per (fwd+adj) pair @1.965GHz" % (B, ms, ms * 1e-3 * 1.965e9 / npair))
 for i, n in enumerate(names):
     print("  %-18s thread0 %8.0f   thread255 %8.0f   cycles/pair" % (n, d[0, i] / npair, d[1, i] / npair))
 print("  total              thread0 %8.0f" % (d[0].sum() / npair))
-print("  a_begin waits per pair: fwdA %.0f fwdB %.0f adjA3 %.0f adjB3 %.0f" % tuple(aw[[0, 1, 2, 5]] / npair))
-sb = dbg.cpu().numpy()[40:44]
-print("  a_end per pair: fences %.0f, syncwarp+arrive %.0f  (4 x NKB blocks per pair)" % (sb[0] / npair, sb[1] / npair))
+mw = dbg.cpu().numpy()[32:34]
+print("  MMA issuer waits per pair: operand A (element threads) %.0f, operand B (weight stream) %.0f" % (mw[0] / npair, mw[1] / npair))
