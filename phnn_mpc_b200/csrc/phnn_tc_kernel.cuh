@@ -33,11 +33,19 @@
 //     K-block loops wait for the MMA most of the time): the g1 half of xbar and half of the R_net
 //     backward chain ride in the da1 loop, the other half of the R_net chain in the e2 loop.
 //
-// Roles: warps 0-7 element threads (256), warp 8 MMA issuer (one lane), warp 9 weight producer.
+// Roles: warps 0 .. 4 NQ - 1 element threads (NQ per instance), then the MMA issuer warp (one lane) and the
+// weight producer warp.
 #pragma once
 #include "phnn_kernel.cuh"
 
 namespace phnn {
+
+// element threads per instance: each owns 32/NQ of every 32 hidden units.  4 (16 element warps, 96 registers) was
+// measured 6 % slower than 2: the per-block time of the producing loops is set by the hand-off chain, not by the
+// number of warps an SM sub-partition can switch between, and the per-instance work is replicated NQ times
+#ifndef PHNN_TC_NQ
+#define PHNN_TC_NQ 2
+#endif
 
 template <int MK_, int NS_, int HID_>
 struct TcShape {
@@ -45,6 +53,11 @@ struct TcShape {
     static constexpr int MK = MK_, NS = NS_, HID = HID_, NN = NS * NS;
     static constexpr bool HAS_R = (MK != MK_CANON);
     static constexpr int TM = 128;         // instances per tile (UMMA M)
+    static constexpr int NQ = PHNN_TC_NQ;  // element threads per instance
+    static constexpr int UP = 32 / NQ;     // hidden units of a K-block per thread
+    static constexpr int CQ = UP / 4;      // 4-unit chunks (float4 of the A ring / tape) of a K-block per thread
+    static constexpr int PP = UP / 2;      // pairs of a K-block per thread
+    static constexpr int NEW = 4 * NQ;     // element warps
     static constexpr int NKB = HID / 32;   // K-blocks of 32 tf32 (one 128-byte swizzle row)
     static constexpr int A_TILE = TM * 128;   // bytes of one A K-block (hi or lo)
     static constexpr int B_TILE = HID * 128;  // bytes of one B K-block (hi or lo)
@@ -67,13 +80,13 @@ struct TcShape {
     static constexpr int OFF_B = OFF_A + NAS * 2 * A_TILE;    // NBE entries
     static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE;
     static constexpr int OFF_XCH = OFF_SMALL + SMALL * 4;
-    static constexpr int SMEM_BYTES = OFF_XCH + XW * 256 * 4;
+    static constexpr int SMEM_BYTES = OFF_XCH + XW * 128 * NQ * 4;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     // barrier indices
     static constexpr int B_AFULL = 0, B_AEMPTY = NAS, B_BFULL = 2 * NAS, B_BEMPTY = 2 * NAS + NBE, B_ACC = 2 * NAS + 2 * NBE,
                          B_SMALL = B_ACC + 2;
     static_assert((B_SMALL + 1) * 8 <= 128, "barriers live in the first 128 bytes");
-    static constexpr int THREADS = 320;
+    static constexpr int THREADS = 128 * NQ + 64;
 };
 
 // big-blob layout for the tensor path: [P: 0 = W2 (B[n=j][k]), 1 = W2^T (B[n=k][K=j])][kb][hi|lo][B_TILE]
@@ -125,35 +138,46 @@ __device__ __forceinline__ float tanh_tc(float x) {
 // keeps the compiler from hoisting the next chunk's loads above this point: without it ptxas
 // front-loads a whole K-block of weight loads and then serialises the tanh chains on one register
 __device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
-// asynchronous TMEM load of 16 consecutive columns of this thread's lane; the registers are
-// valid only after tmem_wait16 (which also ties them to the wait for the compiler)
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+// asynchronous TMEM load of N (16 or 8) consecutive columns of this thread's lane; the registers are
+// valid only after tmem_wait (which also ties them to the wait for the compiler)
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait(uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
                    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                  :
                  : "memory");
 }
+__device__ __forceinline__ void tmem_wait(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
 // visit the NKB 32-column blocks of an accumulator with the next block's load in flight while
-// the current one is processed: body(block index, 16 values of this thread's half)
-template <int NKB, class F>
+// the current one is processed: body(block index, the UP values of this thread's share of the block)
+template <int NKB, int UP, class F>
 __device__ __forceinline__ void for_acc_blocks(uint32_t tacc, F&& body) {
-    uint32_t ra[16], rb[16];
-    tmem_ld16_issue(tacc, ra);
+    uint32_t ra[UP], rb[UP];
+    tmem_ld_issue(tacc, ra);
 #pragma unroll 1
     for (int b = 0; b < NKB; b += 2) {
-        tmem_wait16(ra);
-        tmem_ld16_issue(tacc + (b + 1) * 32, rb);
+        tmem_wait(ra);
+        tmem_ld_issue(tacc + (b + 1) * 32, rb);
         body(b, ra);
-        tmem_wait16(rb);
-        if (b + 2 < NKB) tmem_ld16_issue(tacc + (b + 2) * 32, ra);
+        tmem_wait(rb);
+        if (b + 2 < NKB) tmem_ld_issue(tacc + (b + 2) * 32, ra);
         body(b + 1, rb);
     }
 }
@@ -207,23 +231,11 @@ __device__ __forceinline__ float2 tanh_tc2(float2 x) {
 #define TCP_MARK(c, i) do { } while (0)
 #endif
 
-// scheduling fence granularity in 4-unit chunks: 4 = one fence per K-block (measured 4.8 % faster than 1)
 #ifndef PHNN_TC_PROD_SLEEP
 #define PHNN_TC_PROD_SLEEP 128
 #endif
 #ifndef PHNN_TC_MMA_SLEEP
 #define PHNN_TC_MMA_SLEEP 128
-#endif
-#ifndef PHNN_TC_FENCE_EVERY
-#define PHNN_TC_FENCE_EVERY 4
-#endif
-// balance of the R_net work between the loops that feed the tensor pipe (units per K-block, of a thread's 16):
-// forward units done in the a1 loop (the rest in the a2 loop), backward units done in the da1 loop (the rest in the e2 loop)
-#ifndef PHNN_TC_RF_A
-#define PHNN_TC_RF_A 8
-#endif
-#ifndef PHNN_TC_RB_A
-#define PHNN_TC_RB_A 8
 #endif
 #ifndef PHNN_TC_RFENCE
 #define PHNN_TC_RFENCE 4
@@ -242,14 +254,14 @@ struct TcCtx {
     static constexpr int TW = SH::TM;
     __device__ static int ws_extra(const KParams& p) { return tc_ws_extra(SH::HID, p.T, p.S); }
     __device__ __forceinline__ void set_eval(int e) { ev = e; }
-    int row, hf, lane, barid;
+    int row, qt, lane, barid;  // instance (= TMEM lane), which 1/NQ of every K-block, lane, named barrier of my instance group
     uint32_t tlane;  // TMEM base address with this warp's lane quadrant
     uint32_t ablk;   // A K-blocks produced so far
     uint32_t qdone;  // products whose accumulator this thread has waited for
     int split;       // 3 = 3xTF32, 1 = plain TF32
     float* sck;      // per tile: R_net sums [0,10) and grad H [10,14) of every forward evaluation, [T*S][16][128]
     int ev;          // index of the evaluation in flight (t * S + s)
-    float* tape;     // per CTA: a2, a1, g1 of every forward evaluation of the unit in flight, each [NKB][2][4][128]
+    float* tape;     // per CTA: a2, a1, g1 of every forward evaluation of the unit in flight, each [NKB][8 chunks][128]
                      // float4 (a warp's 32 rows read/write 512 contiguous bytes); nullptr when no adjoint follows
     bool store;
 #ifdef PHNN_TC_PROFILE
@@ -258,9 +270,10 @@ struct TcCtx {
 #endif
 
     __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(phnn_smem); }
+    // (the records were also tried in the kernel parameter block / constant bank, read with LDC.64: 20 % slower)
     __device__ __forceinline__ const float* small() const { return reinterpret_cast<const float*>(phnn_smem + SH::OFF_SMALL); }
     __device__ __forceinline__ float* xch() const { return reinterpret_cast<float*>(phnn_smem + SH::OFF_XCH); }
-    __device__ __forceinline__ void gbar() const { group_bar(barid, 64); }
+    __device__ __forceinline__ void gbar() const { group_bar(barid, 32 * SH::NQ); }
 
     // ---- A-operand ring (element threads are the producers) ----
     __device__ __forceinline__ int a_begin() {
@@ -268,9 +281,9 @@ struct TcCtx {
         mbar_wait(&bars()[SH::B_AEMPTY + slot], ((ablk / SH::NAS) & 1u) ^ 1u);
         return slot;
     }
-    // four consecutive hidden units (chunk q of this thread's 16) of the current K-block
+    // four consecutive hidden units (chunk q of this thread's CQ) of the current K-block
     __device__ __forceinline__ void a_put4(int slot, int q, const float (&v)[4]) const {
-        const int ch = hf * 4 + q;
+        const int ch = qt * SH::CQ + q;
         const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
         unsigned char* hi = phnn_smem + SH::OFF_A + (slot * 2) * SH::A_TILE + off;
         float4 h = make_float4(tf32_rn(v[0]), tf32_rn(v[1]), tf32_rn(v[2]), tf32_rn(v[3]));
@@ -294,29 +307,35 @@ struct TcCtx {
         const uint32_t q = qdone++;
         mbar_wait(&bars()[SH::B_ACC + (q & 1u)], (q >> 1) & 1u);
         tc_fence_after();
-        return tlane + (q & 1u) * SH::HID + hf * 16;
+        return tlane + (q & 1u) * SH::HID + qt * SH::UP;
     }
     // float4 slot of (tape array which: 0 a2, 1 a1, 2 g1; K-block jb; chunk q) of evaluation ev for this thread
     static constexpr size_t TAPE_ARR4 = (size_t)SH::NKB * 8 * 128;  // float4 per array
     __device__ __forceinline__ float4* tape4(int which, int jb, int q) const {
-        return reinterpret_cast<float4*>(tape) + ((size_t)ev * 3 + which) * TAPE_ARR4 + ((jb * 2 + hf) * 4 + q) * 128 + row;
+        return reinterpret_cast<float4*>(tape) + ((size_t)ev * 3 + which) * TAPE_ARR4 + (jb * 8 + qt * SH::CQ + q) * 128 + row;
     }
     // LAST: the final use of these lines (evict-first), otherwise they are read once more soon
     template <bool LAST>
-    __device__ __forceinline__ void tape_load(int which, int jb, float4 (&v)[4]) const {
+    __device__ __forceinline__ void tape_load(int which, int jb, float4 (&v)[SH::CQ]) const {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = LAST ? __ldcs(tape4(which, jb, q)) : __ldcg(tape4(which, jb, q));
+        for (int q = 0; q < SH::CQ; ++q) v[q] = LAST ? __ldcs(tape4(which, jb, q)) : __ldcg(tape4(which, jb, q));
     }
-    // pair exchange: returns mine + partner's for n values starting at slot s0
+    // sum of N values over the NQ threads of an instance, in a fixed order so that the NQ copies of the
+    // instance's state stay bit-identical
     template <int N>
     __device__ __forceinline__ void exchange(float (&v)[N]) {
         float* x = xch();
-        const int t = hf * 128 + row;
+        constexpr int W = 128 * SH::NQ;
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[i * 256 + t] = v[i];
+        for (int i = 0; i < N; ++i) x[i * W + qt * 128 + row] = v[i];
         gbar();
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] += x[i * 256 + (t ^ 128)];
+        for (int i = 0; i < N; ++i) {
+            float a = x[i * W + row];
+#pragma unroll
+            for (int j = 1; j < SH::NQ; ++j) a += x[i * W + j * 128 + row];
+            v[i] = a;
+        }
         gbar();
     }
     __device__ __forceinline__ void begin_unit(const KParams& p, long long tile) {
@@ -372,9 +391,9 @@ __device__ __forceinline__ void pair_scatter(const float4& w01, const float4& w2
 }
 __device__ __forceinline__ float2 one_minus_sq(float2 a) { return sub2(bc2(1.f), mul2(a, a)); }  // one FFMA2
 
-// pair index of (K-block kb, this thread's i-th pair of 8)
+// pair index of (K-block kb, this thread's i-th pair of PP)
 template <class SH>
-__device__ __forceinline__ int tc_pair(const TcCtx<SH>& c, int kb, int i) { return kb * 16 + c.hf * 8 + i; }
+__device__ __forceinline__ int tc_pair(const TcCtx<SH>& c, int kb, int i) { return kb * 16 + c.qt * SH::PP + i; }
 
 // R_net hidden layer and symmetrised output sums for pairs [I0, I1) of this thread's 8 in K-block kb
 template <int I0, int I1, class SH>
@@ -406,21 +425,24 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
     const float* rA = c.small() + SH::O_RA;
 #pragma unroll 1
     for (int kb = 0; kb < SH::NKB; ++kb) {
-        const int slot = c.a_begin();
+        // the block is computed into registers before the wait for its ring slot (which frees when the MMA of
+        // block kb - 2 retires): the arithmetic overlaps the wait instead of following it
+        float av[SH::CQ][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float av[4];
+        for (int q = 0; q < SH::CQ; ++q) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const float* r = rA + tc_pair(c, kb, q * 2 + e) * SH::RA;
                 const float2 a = tanh_tc2(pair_affine(lds4(r), lds4(r + 4), z, lds2(r + 8)));
-                av[2 * e] = a.x; av[2 * e + 1] = a.y;
+                av[q][2 * e] = a.x; av[q][2 * e + 1] = a.y;
             }
-            if (c.tape) *c.tape4(1, kb, q) = make_float4(av[0], av[1], av[2], av[3]);  // read back in phase C
-            c.a_put4(slot, q, av);
+            if (c.tape) *c.tape4(1, kb, q) = make_float4(av[q][0], av[q][1], av[q][2], av[q][3]);  // read back in phase C
         }
+        const int slot = c.a_begin();
+#pragma unroll
+        for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, av[q]);
         c.a_end(slot);
-        if constexpr (SH::HAS_R) tc_rfwd_pairs<0, PHNN_TC_RF_A / 2>(c, kb, y, Sp2);
+        if constexpr (SH::HAS_R) tc_rfwd_pairs<0, SH::PP / 2>(c, kb, y, Sp2);
     }
 }
 
@@ -466,11 +488,11 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
         const uint32_t tacc = c.acc_wait();
         TCP_MARK(c, 1);
         float2 Hp2 = make_float2(0.f, 0.f);
-        for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&zr)[16]) {
-            const int slot = c.a_begin();
+        for_acc_blocks<NKB, SH::UP>(tacc, [&](int jb, const uint32_t (&zr)[SH::UP]) {
+            float dv[SH::CQ][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float dv[4], a2v[4];
+            for (int q = 0; q < SH::CQ; ++q) {
+                float a2v[4];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const float4 m = lds4(rA + tc_pair(c, jb, q * 2 + e) * SH::RA + 12);  // {b2 pair, w3 pair}
@@ -479,15 +501,16 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
                     Hp2 = fma2(zw(m), a2, Hp2);
                     const float2 d = mul2(one_minus_sq(a2), zw(m));
                     a2v[2 * e] = a2.x; a2v[2 * e + 1] = a2.y;
-                    dv[2 * e] = d.x; dv[2 * e + 1] = d.y;
+                    dv[q][2 * e] = d.x; dv[q][2 * e + 1] = d.y;
                 }
                 if (c.tape) __stcs(c.tape4(0, jb, q), make_float4(a2v[0], a2v[1], a2v[2], a2v[3]));
-                c.a_put4(slot, q, dv);
-                if (PHNN_TC_FENCE_EVERY == 1 || (q % PHNN_TC_FENCE_EVERY) == PHNN_TC_FENCE_EVERY - 1) sched_fence();
             }
+            const int slot = c.a_begin();
+#pragma unroll
+            for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, dv[q]);
             c.a_end(slot);
             // the rest of the R_net forward pairs rides here: this loop otherwise waits for the MMA
-            if constexpr (SH::HAS_R) tc_rfwd_pairs<PHNN_TC_RF_A / 2, 8>(c, jb, y, Sp2);
+            if constexpr (SH::HAS_R) tc_rfwd_pairs<SH::PP / 2, SH::PP>(c, jb, y, Sp2);
         });
         X[12] = Hp2.x + Hp2.y;
     }
@@ -501,15 +524,15 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
         for (int i = 0; i < 4; ++i) G2[i] = make_float2(0.f, 0.f);
         if (c.tape) {
             // a1 comes back from the tape (written by this thread in phase A, still in L2)
-            float4 an[4];
+            float4 an[SH::CQ];
             c.tape_load<false>(1, 0, an);
-            for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
-                float4 ac[4];
+            for_acc_blocks<NKB, SH::UP>(tacc, [&](int kb, const uint32_t (&gr)[SH::UP]) {
+                float4 ac[SH::CQ];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ac[q] = an[q];
+                for (int q = 0; q < SH::CQ; ++q) ac[q] = an[q];
                 if (kb + 1 < NKB) c.tape_load<false>(1, kb + 1, an);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < SH::CQ; ++q) {
                     __stcs(c.tape4(2, kb, q), make_float4(__uint_as_float(gr[q * 4]), __uint_as_float(gr[q * 4 + 1]),
                                                           __uint_as_float(gr[q * 4 + 2]), __uint_as_float(gr[q * 4 + 3])));
 #pragma unroll
@@ -522,9 +545,9 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
                 }
             });
         } else {
-            for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&gr)[16]) {
+            for_acc_blocks<NKB, SH::UP>(tacc, [&](int kb, const uint32_t (&gr)[SH::UP]) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < SH::PP; ++i) {
                     const float* r = rA + tc_pair(c, kb, i) * SH::RA;
                     const float4 w01 = lds4(r), w23 = lds4(r + 4);
                     const float2 a1 = tanh_tc2(pair_affine(w01, w23, z, lds2(r + 8)));
@@ -673,24 +696,21 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     // ---- A3: da1 = s1 * (W1 w) -> product 1 (dz2 = W2 da1), with the g1 half of xbar_H (sdot1 * g1) and part
     //      of the R_net chain in the same loop (the loop runs at the pace of the MMA) ----
     {
-        float4 an[4], gn[4];
+        float4 an[SH::CQ], gn[SH::CQ];
         c.tape_load<false>(1, 0, an);
         c.tape_load<true>(2, 0, gn);
 #pragma unroll 1
         for (int kb = 0; kb < NKB; ++kb) {
-            float4 ac[4], gc[4];
+            float4 ac[SH::CQ], gc[SH::CQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { ac[q] = an[q]; gc[q] = gn[q]; }
-#ifndef PHNN_TC_LOAD_AFTER
+            for (int q = 0; q < SH::CQ; ++q) { ac[q] = an[q]; gc[q] = gn[q]; }
             if (kb + 1 < NKB) {
                 c.tape_load<false>(1, kb + 1, an);
                 c.tape_load<true>(2, kb + 1, gn);
             }
-#endif
-            const int slot = c.a_begin();
+            float av[SH::CQ][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float av[4];
+            for (int q = 0; q < SH::CQ; ++q) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const float* r = rA + tc_pair(c, kb, q * 2 + e) * SH::RA;
@@ -699,22 +719,16 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
                     const float2 g1 = e ? zw(gc[q]) : xy(gc[q]);
                     const float2 da = mul2(one_minus_sq(a1), pair_linear(w01, w23, w));
                     pair_scatter(w01, w23, mul2(mul2(a1, da), g1), T2);
-                    av[2 * e] = da.x; av[2 * e + 1] = da.y;
+                    av[q][2 * e] = da.x; av[q][2 * e + 1] = da.y;
                 }
-                c.a_put4(slot, q, av);
             }
+            const int slot = c.a_begin();
+#pragma unroll
+            for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, av[q]);
             c.a_end(slot);
-#ifdef PHNN_TC_LOAD_AFTER
-            // the next block's tape loads go out after the hand-off: the fence / release of a_end waits for
-            // every outstanding load of the thread, so loads issued before it are not a prefetch
-            if (kb + 1 < NKB) {
-                c.tape_load<false>(1, kb + 1, an);
-                c.tape_load<true>(2, kb + 1, gn);
-            }
-#endif
             if constexpr (SH::HAS_R) {
 #pragma unroll
-                for (int i = 0; i < PHNN_TC_RB_A / 2; ++i) {
+                for (int i = 0; i < SH::PP / 2; ++i) {
                     tc_rback_pair(c, tc_pair(c, kb, i), y, Rb, X2);
                     if (i % 2 == 1) sched_fence();
                 }
@@ -724,40 +738,36 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     TCP_MARK(c, 6);
     // ---- B3: e2 = -2 a2 da2 w3 -> product 2 (dg1 = W2^T e2); the rest of the R_net chain ----
     {
-        float4 an[4];
+        float4 an[SH::CQ];
         c.tape_load<true>(0, 0, an);
         const uint32_t tacc = c.acc_wait();
         TCP_MARK(c, 7);
-        for_acc_blocks<NKB>(tacc, [&](int jb, const uint32_t (&dz)[16]) {
-            float4 a2q[4];
+        for_acc_blocks<NKB, SH::UP>(tacc, [&](int jb, const uint32_t (&dz)[SH::UP]) {
+            float4 a2q[SH::CQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) a2q[q] = an[q];
-#ifndef PHNN_TC_LOAD_AFTER
+            for (int q = 0; q < SH::CQ; ++q) a2q[q] = an[q];
             if (jb + 1 < NKB) c.tape_load<true>(0, jb + 1, an);
-#endif
-            const int slot = c.a_begin();
+            float ev[SH::CQ][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float ev[4];
+            for (int q = 0; q < SH::CQ; ++q) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const float2 m2w3 = lds2(rA + tc_pair(c, jb, q * 2 + e) * SH::RA + 16);  // -2 w3 pair
                     const float2 a2 = e ? zw(a2q[q]) : xy(a2q[q]);
                     const float2 dzz = make_float2(__uint_as_float(dz[q * 4 + 2 * e]), __uint_as_float(dz[q * 4 + 2 * e + 1]));
                     const float2 ee = mul2(mul2(a2, mul2(one_minus_sq(a2), dzz)), m2w3);
-                    ev[2 * e] = ee.x; ev[2 * e + 1] = ee.y;
+                    ev[q][2 * e] = ee.x; ev[q][2 * e + 1] = ee.y;
                 }
-                c.a_put4(slot, q, ev);
             }
+            const int slot = c.a_begin();
+#pragma unroll
+            for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, ev[q]);
             c.a_end(slot);
-#ifdef PHNN_TC_LOAD_AFTER
-            if (jb + 1 < NKB) c.tape_load<true>(0, jb + 1, an);
-#endif
             if constexpr (SH::HAS_R) {
 #pragma unroll
-                for (int i = PHNN_TC_RB_A / 2; i < 8; ++i) {
+                for (int i = SH::PP / 2; i < SH::PP; ++i) {
                     tc_rback_pair(c, tc_pair(c, jb, i), y, Rb, X2);
-                    if ((i - PHNN_TC_RB_A / 2) % 2 == 1) sched_fence();
+                    if ((i - SH::PP / 2) % 2 == 1) sched_fence();
                 }
             }
         });
@@ -765,17 +775,17 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     TCP_MARK(c, 8);
     // ---- C4: the dg1 half of xbar_H ----
     {
-        float4 an[4];
+        float4 an[SH::CQ];
         c.tape_load<true>(1, 0, an);
         const uint32_t tacc = c.acc_wait();
         TCP_MARK(c, 9);
-        for_acc_blocks<NKB>(tacc, [&](int kb, const uint32_t (&dg)[16]) {
-            float4 ac[4];
+        for_acc_blocks<NKB, SH::UP>(tacc, [&](int kb, const uint32_t (&dg)[SH::UP]) {
+            float4 ac[SH::CQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ac[q] = an[q];
+            for (int q = 0; q < SH::CQ; ++q) ac[q] = an[q];
             if (kb + 1 < NKB) c.tape_load<true>(1, kb + 1, an);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < SH::CQ; ++q) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const float* r = rA + tc_pair(c, kb, q * 2 + e) * SH::RA;
@@ -822,13 +832,14 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
 // Work-stealing schedule of the solve: (tile, iteration) units from a global counter.  All per-instance
 // state that crosses iterations (U, Adam moments, best controls, best cost) lives in global memory and is
 // read with ld.cg, so any CTA can run any iteration of any tile once the previous iteration of that tile
-// has been published.  next() is called by all 320 threads of the CTA (it contains CTA barriers).
+// has been published.  next() is called by all threads of the CTA (it contains CTA barriers).
 struct StealSched {
     int* counter;
     int* progress;
     long long tiles;
     int iters;
     int* slot;  // shared-memory broadcast slot
+    int nelem;  // element threads of the CTA
     static constexpr bool kStateInWorkspace = true;
     __device__ __forceinline__ long long tile0() const { return -1; }
     __device__ __forceinline__ int grab() {
@@ -859,7 +870,7 @@ struct StealSched {
     }
     template <class ENG>
     __device__ __forceinline__ void done(ENG&, const Unit& u) {
-        group_bar(6, 256);  // all element threads have issued their global writes of this unit
+        group_bar(6, nelem);  // all element threads have issued their global writes of this unit
         if (threadIdx.x == 0) {
             __threadfence();
             *reinterpret_cast<volatile int*>(progress + u.tile) = u.it;
@@ -892,14 +903,14 @@ struct StridedSched {
 // the kernel
 // ---------------------------------------------------------------------------------------
 template <int MK, int NS, int HID>
-__global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(TcShape<MK, NS, HID>::THREADS, 1) phnn_tc_kernel(const __grid_constant__ KParams p) {
     using SH = TcShape<MK, NS, HID>;
     uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int e = 0; e < SH::NAS; ++e) {
-            mbar_init(&bars[SH::B_AFULL + e], 8);
+            mbar_init(&bars[SH::B_AFULL + e], SH::NEW);
             mbar_init(&bars[SH::B_AEMPTY + e], 1);
         }
         for (int e = 0; e < SH::NBE; ++e) {
@@ -912,7 +923,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == SH::NEW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                      "r"((uint32_t)SH::TMEM_COLS)
                      : "memory");
@@ -943,26 +954,26 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
     const size_t tape_eval = (size_t)3 * HID * 128;  // floats per taped evaluation
     float* const tape = (p.tape && nadj > 0) ? p.tape + (size_t)blockIdx.x * E * tape_eval : nullptr;
     const int split = p.tc_split;
-    StealSched ss{p.sched, p.sched + 1, p.tiles, p.iters, reinterpret_cast<int*>(phnn_smem + 768)};
+    StealSched ss{p.sched, p.sched + 1, p.tiles, p.iters, reinterpret_cast<int*>(phnn_smem + 768), 128 * SH::NQ};
 
-    if (warp < 8) {
+    if (warp < SH::NEW) {
         // ===== element threads =====
         TcCtx<SH> c;
         c.row = threadIdx.x & 127;
-        c.hf = threadIdx.x >> 7;
+        c.qt = threadIdx.x >> 7;
         c.lane = lane;
         c.barid = 1 + (warp & 3);
         c.tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
         c.ablk = 0;
         c.qdone = 0;
         c.split = split;
-        c.store = (c.hf == 0);
+        c.store = (c.qt == 0);
         c.tape = tape;
         c.sck = nullptr;
         c.ev = 0;
         mbar_wait(&bars[SH::B_SMALL], 0);
 #ifdef PHNN_TC_PROFILE
-        c.prof = (threadIdx.x == 0 || threadIdx.x == 255) ? reinterpret_cast<unsigned long long*>(phnn_smem + 128) + (threadIdx.x ? 16 : 0) : nullptr;
+        c.prof = (threadIdx.x == 0 || threadIdx.x == 128 * SH::NQ - 1) ? reinterpret_cast<unsigned long long*>(phnn_smem + 128) + (threadIdx.x ? 16 : 0) : nullptr;
         if (c.prof)
             for (int i = 0; i < 16; ++i) c.prof[i] = 0;
         c.tlast = (unsigned)clock();
@@ -978,7 +989,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         if (blockIdx.x == 0 && c.prof && p.dbg)
             for (int i = 0; i < 16; ++i) p.dbg[(threadIdx.x ? 16 : 0) + i] = (long long)c.prof[i];
 #endif
-    } else if (warp == 8) {
+    } else if (warp == SH::NEW) {
         // ===== MMA issuer =====
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t a_base = smem_u32(phnn_smem + SH::OFF_A), b_base = smem_u32(phnn_smem + SH::OFF_B);
@@ -1104,7 +1115,7 @@ __global__ void __launch_bounds__(320, 1) phnn_tc_kernel(const __grid_constant__
         }
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == SH::NEW) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"((uint32_t)SH::TMEM_COLS) : "memory");
     }
