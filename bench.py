@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override instances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--tensor-mode", type=int, default=-1, help="0 FP32-FMA kernel, 3 tcgen05 3xTF32 (default), 1 tcgen05 TF32")
+    ap.add_argument("--tensor-mode", type=int, default=-1, help="0 FP32-FMA kernel, 2 tcgen05 TF32 + BF16 correction product (default), 3 tcgen05 3xTF32, 1 tcgen05 plain TF32")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.batch:
@@ -325,7 +325,7 @@ def main():
     except Exception:
         pass
     tmode = pk.get_option("tensor_mode")
-    uses_tc = tmode in (1, 3) and B >= pk.get_option("tensor_min_batch")
+    uses_tc = tmode in (1, 2, 3) and B >= pk.get_option("tensor_min_batch")
     traffic = None
     try:
         tr = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
@@ -338,12 +338,17 @@ def main():
         pass
     if uses_tc:
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        split = 3 if tmode == 3 else 1
         # tensor work actually issued: per evaluation 2 (forward) + 2 (adjoint: the two Hessian-vector products; the
-        # forward activations come back from the tape) products of 128 x h x h MACs per 128-instance tile, each as
-        # `split` TF32 MMAs
+        # forward activations come back from the tape) products of 128 x h x h MACs per 128-instance tile.  Mode 3
+        # issues each as 3 TF32 MMAs; mode 2 as 1 TF32 MMA + one BF16 product of twice the depth ([a_lo | a] x [b | b_lo]);
+        # mode 1 as 1 TF32 MMA.  BF16 MMAs run at twice the TF32 rate, so the time at peak rate is counted in TF32 units.
         tiles = (B + 127) // 128
-        mma_flops = tiles * iters * H * S * (2 + 2) * split * 2.0 * 128 * h * h
+        base = tiles * iters * H * S * (2 + 2) * 2.0 * 128 * h * h
+        tf32_flops = base * (3 if tmode == 3 else 1)
+        bf16_flops = base * 2 if tmode == 2 else 0.0
+        mma_flops = tf32_flops + bf16_flops
+        tf32_equiv_flops = tf32_flops + bf16_flops / 2
+        scheme = {3: "3xTF32 error-compensated", 2: "TF32 + BF16 correction product (FP32-level accuracy)", 1: "plain TF32"}[tmode]
         # HBM side of the same kernel: the activation tape (a1, a2, g1: 3 h floats per instance and evaluation) is
         # written by the forward sweep and read back by the adjoint
         tape_bytes = tiles * iters * H * S * 2.0 * 3 * h * 128 * 4
@@ -353,21 +358,22 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, this pool)" if peaks else
                                    "fallback 1400 (B200_PROFILING.md)",
                     "algorithmic_flops_per_launch": algo,
-                    "kernel": "phnn_tc_kernel<MK,NS,HID> (tcgen05 kind::tf32, %s), one launch per step" % (
-                        "3xTF32 error-compensated" if split == 3 else "plain TF32"),
+                    "kernel": "phnn_tc_kernel<MK,NS,HID> (tcgen05 kind::tf32%s, %s), one launch per step" % (
+                        " + kind::f16" if tmode == 2 else "", scheme),
                     "kernel_ms": kernel_ms,
                     "executed_tensor_tflops": mma_flops / (kernel_ms * 1e-3) / 1e12,
                     "tf32_mma_peak_tflops": tf32_peak,
-                    "tensor_pipe_frac": mma_flops / (kernel_ms * 1e-3) / 1e12 / tf32_peak,
+                    "tensor_pipe_frac": tf32_equiv_flops / (kernel_ms * 1e-3) / 1e12 / tf32_peak,
                     "executed_over_algorithmic": mma_flops / algo,
                     "fp32_fma_peak_tflops": fp32_peak, "frac_of_fp32_fma_peak": achieved / fp32_peak,
                     "hbm": {"algorithmic_tape_bytes_per_launch": tape_bytes,
                             "achieved_gbps": tape_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbps": hbm_peak,
                             "frac": tape_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                             "measured_dram_bytes_per_launch": traffic},
-                    "note": "FP32-level accuracy on TF32 tensor cores costs 3 MMAs per product at half the bf16 rate: "
-                            "frac vs the bf16 peak is bounded by 1/6=0.17; the adjoint reads the forward activations "
-                            "from an HBM tape instead of recomputing them (4 tensor products per pair instead of 6)"}
+                    "note": "FP32-level accuracy on the tensor cores costs one TF32 product (half the bf16 rate) plus a BF16 "
+                            "correction product of twice the depth: frac vs the bf16 peak is bounded by 1/4; the adjoint "
+                            "reads the forward activations from an HBM tape instead of recomputing them (4 tensor products "
+                            "per pair instead of 6); the binding resource is the L1/shared-memory data pipe (DESIGN.md 4a)"}
     else:
         roofline = {"bound": "fp32-fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak, "traffic": traffic,
@@ -414,7 +420,7 @@ def main():
     line = {"metric": "cartpole_mpc_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, kernel_path=("tcgen05-3xTF32" if tmode == 3 else "tcgen05-TF32") if uses_tc else "fp32-fma",
+            "config": dict(config, kernel_path={3: "tcgen05-3xTF32", 2: "tcgen05-TF32+BF16corr", 1: "tcgen05-TF32"}[tmode] if uses_tc else "fp32-fma",
                            l2="256 MiB buffer written between timed steps (L2 flush); per-step working set "
                                       "(stage checkpoints) also exceeds L2", gather_ms=gather_ms),
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu, "rollout": rollout_metric,

@@ -77,8 +77,9 @@ int phnn_pack_destroy(phnn_pack *pack);
 int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
 
 /* Kernel selection knobs (no reference counterpart).
- *   "tensor_mode"      0: FP32-FMA kernel only; 3 (default where built): tcgen05 tensor cores with
- *                      3xTF32 error compensation (FP32-level accuracy); 1: plain TF32 (looser).
+ *   "tensor_mode"      0: FP32-FMA kernel only; 2 (default where built): tcgen05 tensor cores, TF32 product + one
+ *                      BF16 correction product (FP32-level accuracy); 3: 3xTF32 error compensation (FP32-level
+ *                      accuracy, 1.5x the tensor work); 1: plain TF32 (looser).
  *   "tensor_min_batch" smallest B routed to the tcgen05 kernel (default 1: it beats the FP32-FMA kernel
  *                      at every batch size; small batches go to the latency kernel first).
  *   "latency_max_batch" largest B routed to the one-CTA-per-instance latency kernel (default 6-64 x SM

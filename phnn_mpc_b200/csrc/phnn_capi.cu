@@ -18,13 +18,15 @@ using namespace phnn;
 struct phnn_pack {
     int abi_kind, mk, n, m, h;
     int device, num_sms;
-    int tc_mode;          // 0: FP32-FMA kernel only; 3: tcgen05 3xTF32 when eligible; 1: tcgen05 plain TF32
+    int tc_mode;          // 0: FP32-FMA kernel only; tcgen05 kernel when eligible: 3 = 3xTF32, 2 = TF32 + BF16 correction
+                          // product, 1 = plain TF32
     long tc_min_batch;    // smallest B routed to the tcgen05 kernel
     long lat_max_batch;   // largest B routed to the one-CTA-per-instance latency kernel (0 = never)
     float* d_small;
     float* d_big;
     unsigned char* d_wtc;
     float* d_small_tc;
+    unsigned char* d_wtc2;  // tensor_mode 2 weights (TF32 hi tiles + BF16 correction tiles)
     size_t small_floats;
     KParams base;  // model constants filled in once
 };
@@ -135,6 +137,37 @@ static void fill_tc_big(const phnn_model_desc* d, std::vector<unsigned char>& ou
                 }
 }
 
+static uint16_t bf16_round_host(float x) {  // cvt.rn.bf16.f32 (finite inputs)
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// tensor_mode 2: [P: W2 | W2^T][kb][ TF32 hi tile | BF16 tile of 64 per row = (b (32) | b_lo (32)) ], each h rows x 128 B,
+// K-major SWIZZLE_128B.  The BF16 tile meets the element threads' (a_lo | a) rows in one K = 64 product.
+static void fill_tc_big_bf16(const phnn_model_desc* d, std::vector<unsigned char>& out) {
+    const int h = d->h, nkb = h / 32;
+    const size_t tile = (size_t)h * 128;
+    out.assign((size_t)2 * nkb * 2 * tile, 0);
+    for (int P = 0; P < 2; ++P)
+        for (int kb = 0; kb < nkb; ++kb)
+            for (int n = 0; n < h; ++n)
+                for (int c = 0; c < 32; ++c) {
+                    const int K = kb * 32 + c;
+                    const float val = (P == 0) ? d->W2[(size_t)n * h + K] : d->W2[(size_t)K * h + n];
+                    const float hi = tf32_round_host(val);
+                    const uint16_t b16 = bf16_round_host(val), lo16 = bf16_round_host(val - hi);
+                    const size_t base = ((size_t)(P * nkb + kb) * 2) * tile;
+                    memcpy(&out[base + sw128_off(n, c)], &hi, 4);
+                    // BF16 tile: element column j of 64 sits at byte 2 j of the 128-byte row (16-byte chunk j / 8)
+                    const size_t row = base + tile + (size_t)(n >> 3) * 1024 + (n & 7) * 128;
+                    const int j0 = c, j1 = 32 + c;
+                    memcpy(&out[row + ((((j0 >> 3) ^ (n & 7)) & 7) << 4) + (j0 & 7) * 2], &b16, 2);
+                    memcpy(&out[row + ((((j1 >> 3) ^ (n & 7)) & 7) << 4) + (j1 & 7) * 2], &lo16, 2);
+                }
+}
+
 // pair-interleaved records of the small layers (layout in TcShape): every field is {unit 2P, unit 2P+1}
 static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
     const int h = d->h, n = d->n;   // n == 4 for every tcgen05 shape
@@ -241,11 +274,15 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         std::vector<float> stc;
         fill_tc_big(d, wtc);
         fill_tc_small(d, stc);
+        std::vector<unsigned char> wtc2;
+        fill_tc_big_bf16(d, wtc2);
         e = cudaMalloc(&pk->d_wtc, wtc.size());
+        if (e == cudaSuccess) e = cudaMalloc(&pk->d_wtc2, wtc2.size());
+        if (e == cudaSuccess) e = cudaMemcpy(pk->d_wtc2, wtc2.data(), wtc2.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMalloc(&pk->d_small_tc, stc.size() * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(pk->d_wtc, wtc.data(), wtc.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pk->d_small_tc, stc.data(), stc.size() * sizeof(float), cudaMemcpyHostToDevice);
-        pk->tc_mode = 3;
+        pk->tc_mode = 2;  // TF32 + BF16 correction product: FP32-level accuracy at 2/3 of the MMA work of 3xTF32
         pk->tc_min_batch = 1;  // measured: the tcgen05 kernel beats the FP32-FMA kernel at every batch size (tools/gpu_crossover.py)
     }
     cudaSetDevice(prev);
@@ -253,6 +290,7 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         cudaFree(pk->d_small);
         cudaFree(pk->d_big);
         cudaFree(pk->d_wtc);
+        cudaFree(pk->d_wtc2);
         cudaFree(pk->d_small_tc);
         delete pk;
         return cuda_fail(e, "phnn_pack_create");
@@ -292,6 +330,7 @@ extern "C" int phnn_pack_destroy(phnn_pack* pk) {
     cudaFree(pk->d_small);
     cudaFree(pk->d_big);
     cudaFree(pk->d_wtc);
+    cudaFree(pk->d_wtc2);
     cudaFree(pk->d_small_tc);
     delete pk;
     return 0;
@@ -300,7 +339,7 @@ extern "C" int phnn_pack_destroy(phnn_pack* pk) {
 extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) {
     if (!pk || !key) return fail(PHNN_E_ARG, "phnn_pack_set_option: null argument");
     if (!strcmp(key, "tensor_mode")) {
-        if (value != 0 && value != 1 && value != 3) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1 or 3");
+        if (value != 0 && value != 1 && value != 2 && value != 3) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1, 2 or 3");
         if (value != 0 && !pk->d_wtc) return fail(PHNN_E_UNSUPPORTED, "no tcgen05 kernel for this model shape");
         pk->tc_mode = (int)value;
         return 0;
@@ -391,7 +430,8 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     const long long tiles = (P.B + SH::TM - 1) / SH::TM;
     auto kern = phnn_tc_kernel<SH::MK, SH::NS, SH::HID>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
-    P.tc_split = pk->tc_mode == 1 ? 1 : 3;
+    P.tc_split = pk->tc_mode;  // 1 plain TF32, 2 TF32 + BF16 correction product, 3 3xTF32
+    if (pk->tc_mode == 2) P.wtc = pk->d_wtc2;
     P.ng = 1;
     P.dbg = g_dbg;
     P.tiles = tiles;

@@ -109,6 +109,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// same for BF16 operands (K = 16 per instruction), FP32 accumulation into the same TMEM accumulator
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+#ifdef PHNN_TC_EXP_NOMMA
+    return;
+#endif
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -208,6 +219,12 @@ PHNN_F32X2_BINOP(add2, "add")
 PHNN_F32X2_BINOP(sub2, "sub")
 #undef PHNN_F32X2_BINOP
 __device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+// {lo, hi} -> one 32-bit word of two round-to-nearest BF16 (lo at the lower address)
+__device__ __forceinline__ uint32_t bf16x2_of(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ float2 xy(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 zw(const float4& v) { return make_float2(v.z, v.w); }
 // tanh_tc on a pair (same operations per element)
@@ -258,7 +275,7 @@ struct TcCtx {
     uint32_t tlane;  // TMEM base address with this warp's lane quadrant
     uint32_t ablk;   // A K-blocks produced so far
     uint32_t qdone;  // products whose accumulator this thread has waited for
-    int split;       // 3 = 3xTF32, 1 = plain TF32
+    int split;       // 3 = 3xTF32, 2 = TF32 + one BF16 correction product (K = 64), 1 = plain TF32
     float* sck;      // per tile: R_net sums [0,10) and grad H [10,14) of every forward evaluation, [T*S][16][128]
     int ev;          // index of the evaluation in flight (t * S + s)
     float* tape;     // per CTA: a2, a1, g1 of every forward evaluation of the unit in flight, each [NKB][8 chunks][128]
@@ -291,6 +308,36 @@ struct TcCtx {
         if (split == 3) {
             const float2 l01 = sub2(make_float2(v[0], v[1]), xy(h)), l23 = sub2(make_float2(v[2], v[3]), zw(h));
             *reinterpret_cast<float4*>(hi + SH::A_TILE) = make_float4(l01.x, l01.y, l23.x, l23.y);
+        }
+    }
+    // split == 2: the correction operand of units [8 q2, 8 q2 + 8) of this thread's UP: the second half of the slot
+    // is one K-major SWIZZLE_128B tile of 64 BF16 per row, [a_lo (32) | a (32)], multiplied against [b | b_lo] rows
+    __device__ __forceinline__ void a_put_corr8(int slot, int q2, const float (&v0)[4], const float (&v1)[4]) const {
+        unsigned char* base = phnn_smem + SH::OFF_A + (slot * 2 + 1) * SH::A_TILE + (row >> 3) * 1024 + (row & 7) * 128;
+        const int ch = qt * (SH::UP / 8) + q2;  // 16-byte chunk (8 BF16) of the lo part; the hi part is 4 chunks further
+        float l0[4], l1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { l0[i] = v0[i] - tf32_rn(v0[i]); l1[i] = v1[i] - tf32_rn(v1[i]); }
+        *reinterpret_cast<uint4*>(base + ((ch ^ (row & 7)) << 4)) =
+            make_uint4(bf16x2_of(l0[0], l0[1]), bf16x2_of(l0[2], l0[3]), bf16x2_of(l1[0], l1[1]), bf16x2_of(l1[2], l1[3]));
+        *reinterpret_cast<uint4*>(base + (((ch + 4) ^ (row & 7)) << 4)) =
+            make_uint4(bf16x2_of(v0[0], v0[1]), bf16x2_of(v0[2], v0[3]), bf16x2_of(v1[0], v1[1]), bf16x2_of(v1[2], v1[3]));
+    }
+    // all UP values of this thread for the K-block: TF32 hi tile + the correction operand of the chosen scheme
+    __device__ __forceinline__ void a_put_block(int slot, const float (&v)[SH::CQ][4]) const {
+        if (split == 2) {
+#pragma unroll
+            for (int q = 0; q < SH::CQ; ++q) {
+                const int ch = qt * SH::CQ + q;
+                const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
+                *reinterpret_cast<float4*>(phnn_smem + SH::OFF_A + (slot * 2) * SH::A_TILE + off) =
+                    make_float4(tf32_rn(v[q][0]), tf32_rn(v[q][1]), tf32_rn(v[q][2]), tf32_rn(v[q][3]));
+            }
+#pragma unroll
+            for (int q2 = 0; q2 < SH::CQ / 2; ++q2) a_put_corr8(slot, q2, v[2 * q2], v[2 * q2 + 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < SH::CQ; ++q) a_put4(slot, q, v[q]);
         }
     }
     __device__ __forceinline__ void a_end(int slot) {
@@ -439,8 +486,7 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
             if (c.tape) *c.tape4(1, kb, q) = make_float4(av[q][0], av[q][1], av[q][2], av[q][3]);  // read back in phase C
         }
         const int slot = c.a_begin();
-#pragma unroll
-        for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, av[q]);
+c.a_put_block(slot, av);
         c.a_end(slot);
         if constexpr (SH::HAS_R) tc_rfwd_pairs<0, SH::PP / 2>(c, kb, y, Sp2);
     }
@@ -506,8 +552,7 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
                 if (c.tape) __stcs(c.tape4(0, jb, q), make_float4(a2v[0], a2v[1], a2v[2], a2v[3]));
             }
             const int slot = c.a_begin();
-#pragma unroll
-            for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, dv[q]);
+c.a_put_block(slot, dv);
             c.a_end(slot);
             // the rest of the R_net forward pairs rides here: this loop otherwise waits for the MMA
             if constexpr (SH::HAS_R) tc_rfwd_pairs<SH::PP / 2, SH::PP>(c, jb, y, Sp2);
@@ -723,8 +768,7 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
                 }
             }
             const int slot = c.a_begin();
-#pragma unroll
-            for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, av[q]);
+c.a_put_block(slot, av);
             c.a_end(slot);
             if constexpr (SH::HAS_R) {
 #pragma unroll
@@ -760,8 +804,7 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
                 }
             }
             const int slot = c.a_begin();
-#pragma unroll
-            for (int q = 0; q < SH::CQ; ++q) c.a_put4(slot, q, ev[q]);
+c.a_put_block(slot, ev);
             c.a_end(slot);
             if constexpr (SH::HAS_R) {
 #pragma unroll
@@ -992,6 +1035,7 @@ __global__ void __launch_bounds__(TcShape<MK, NS, HID>::THREADS, 1) phnn_tc_kern
     } else if (warp == SH::NEW) {
         // ===== MMA issuer =====
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // BF16 x BF16 -> F32
         const uint32_t a_base = smem_u32(phnn_smem + SH::OFF_A), b_base = smem_u32(phnn_smem + SH::OFF_B);
         uint32_t ablk = 0, bent = 0;
         long long qtot = 0;  // products issued so far (accumulator / operand parity continues across units)
@@ -1033,7 +1077,7 @@ __global__ void __launch_bounds__(TcShape<MK, NS, HID>::THREADS, 1) phnn_tc_kern
                         }
                         umma_commit(&bars[SH::B_BEMPTY + e]);
                         ++bent;
-                        if (split == 3) {
+                        if (split != 1) {
                             e = bent % SH::NBE;
 #ifdef PHNN_TC_PROFILE
                             const long long t2 = clock64();
@@ -1044,9 +1088,16 @@ __global__ void __launch_bounds__(TcShape<MK, NS, HID>::THREADS, 1) phnn_tc_kern
 #endif
                             tc_fence_after();
                             b_t = b_base + e * SH::B_TILE;
+                            if (split == 3) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_tf32(acc, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc, 1u);
+                            } else {
+                                // [a_lo | a] (64 BF16 per row) x [b | b_lo]: both correction terms in one K = 64 product
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_bf16(acc, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(b_t + ks * 32), idesc16, 1u);
+                            }
                             umma_commit(&bars[SH::B_BEMPTY + e]);
                             ++bent;
                         }
@@ -1097,7 +1148,7 @@ __global__ void __launch_bounds__(TcShape<MK, NS, HID>::THREADS, 1) phnn_tc_kern
                                 }
                             }
                         }
-                        for (int hl = 0; hl < (split == 3 ? 2 : 1); ++hl) {
+                        for (int hl = 0; hl < (split != 1 ? 2 : 1); ++hl) {
                             const uint32_t e = bent % SH::NBE;
                             mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, PHNN_TC_PROD_SLEEP);
 #if defined(PHNN_TC_EXP_NOB)  // timing experiment (wrong results): no weight traffic at all / none for the lo tiles
