@@ -296,9 +296,10 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         return cuda_fail(e, "phnn_pack_create");
     }
     pk->small_floats = small.size();
-    // crossover measured on B200 (tools/gpu_crossover.py): the latency kernel wins up to ~64 instances per SM at
-    // h = 64, ~14 per SM at h = 128 against the FP32-FMA kernel and ~6 per SM against the tcgen05 kernel
-    pk->lat_max_batch = !has_lat_shape(mk, n, h) ? 0 : (h <= 64 ? 64L : (pk->d_wtc ? 6L : 14L)) * pk->num_sms;
+    // crossover measured on B200 (tools/gpu_crossover.py) with up to 8 (h = 64) / 4 (h = 128) instances per CTA: the
+    // latency kernel wins up to ~100 instances per SM at h = 64, ~34 per SM at h = 128 against the FP32-FMA kernel and
+    // ~8 per SM against the tcgen05 kernel
+    pk->lat_max_batch = !has_lat_shape(mk, n, h) ? 0 : (h <= 64 ? 96L : (pk->d_wtc ? 8L : 32L)) * pk->num_sms;
     KParams& P = pk->base;
     P.wsmall = pk->d_small;
     P.wbig = pk->d_big;
@@ -398,10 +399,14 @@ template <class SH>
 static int launch_lat_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
     auto kern = phnn_lat_kernel<SH::MK, SH::NS, SH::HID>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
-    P.ng = 1;
-    kern<<<(unsigned)P.B, SH::HID, SH::SMEM_BYTES, stream>>>(P);
+    // instances per CTA: one per SM first, stacked (up to NI, sharing the weights in shared memory) only when the batch
+    // exceeds the SM count
+    long long per = (P.B + pk->num_sms - 1) / pk->num_sms;
+    if (per < 1) per = 1;
+    if (per > SH::NI) per = SH::NI;
+    P.ng = (int)per;
+    kern<<<(unsigned)((P.B + per - 1) / per), SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
-    (void)pk;
     return 0;
 }
 

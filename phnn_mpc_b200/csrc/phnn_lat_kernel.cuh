@@ -15,18 +15,31 @@
 
 namespace phnn {
 
+// threads per CTA of the latency kernel (512 = 8 instances at h = 64, 4 at h = 128; 128 registers per thread)
+#ifndef PHNN_LAT_THREADS
+#define PHNN_LAT_THREADS 512
+#endif
+#ifndef PHNN_LAT_MINBLOCKS
+#define PHNN_LAT_MINBLOCKS 1
+#endif
+
 template <int MK_, int NS_, int HID_>
 struct LatShape {
     static constexpr int MK = MK_, NS = NS_, HID = HID_, NN = NS * NS;
     static constexpr bool HAS_R = (MK != MK_CANON);
     static constexpr bool HAS_GNET = (MK == MK_PHNN_GNET);
-    static constexpr int NW = HID / 32;  // warps
+    static constexpr int NW = HID / 32;  // warps per instance
+    // instances per CTA: they share the W2^T | W2 copy in shared memory, which is what limited residency to one
+    // (h = 128) or a handful (h = 64) of instances per SM; each instance keeps its own vectors, reduction
+    // exchange and named barrier
+    static constexpr int THREADS = PHNN_LAT_THREADS;
+    static constexpr int NI = THREADS / HID;
     using FS = Shape<MK, NS, HID>;       // small-weight blob layout of the FP32 kernel
-    // shared memory (floats): W2^T | W2 (2*HID*HID), 4 vectors of HID, reduction exchange [32][NW]
+    // shared memory (floats): W2^T | W2 (2*HID*HID), then per instance 4 vectors of HID and the reduction exchange [32][NW]
     static constexpr int O_W = 0;
     static constexpr int O_V = 2 * HID * HID;
-    static constexpr int O_PART = O_V + 4 * HID;
-    static constexpr int FLOATS = O_PART + 32 * NW;
+    static constexpr int PER = 4 * HID + 32 * NW;
+    static constexpr int FLOATS = O_V + NI * PER;
     static constexpr size_t SMEM_BYTES = 128 + sizeof(float) * (size_t)FLOATS;
     static_assert(SMEM_BYTES <= 232448, "W2 and W2^T must fit in shared memory (h <= 128)");
 };
@@ -62,7 +75,7 @@ struct LatCtx {
     static constexpr int TW = 1;
     __device__ static int ws_extra(const KParams&) { return 0; }
     __device__ __forceinline__ void set_eval(int) {}
-    int k, lane, warp;
+    int k, lane, warp, inst;  // hidden unit, lane, warp within the instance, instance slot of the CTA
     bool store;
     // this hidden unit's rows of the small layers
     float w1[SH::NS], b1, b2, w3;
@@ -72,9 +85,9 @@ struct LatCtx {
     __device__ __forceinline__ float* smf() const { return reinterpret_cast<float*>(phnn_smem + 128); }
     __device__ __forceinline__ const float* W2T() const { return smf() + SH::O_W; }
     __device__ __forceinline__ const float* W2() const { return smf() + SH::O_W + SH::HID * SH::HID; }
-    __device__ __forceinline__ float* vec(int i) const { return smf() + SH::O_V + i * SH::HID; }
-    __device__ __forceinline__ float* part() const { return smf() + SH::O_PART; }
-    __device__ __forceinline__ void gbar() const { __syncthreads(); }
+    __device__ __forceinline__ float* vec(int i) const { return smf() + SH::O_V + inst * SH::PER + i * SH::HID; }
+    __device__ __forceinline__ float* part() const { return smf() + SH::O_V + inst * SH::PER + 4 * SH::HID; }
+    __device__ __forceinline__ void gbar() const { group_bar(1 + inst, SH::HID); }  // the threads of my instance
     __device__ __forceinline__ void begin_unit(const KParams&, long long) {}
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
         lat_eval_fwd(*this, p, y, u, f, H);
@@ -84,12 +97,12 @@ struct LatCtx {
         lat_eval_vjp(*this, p, y, u, v, xbar, ubar);
     }
     // block totals of the first V of 32 per-thread values; every thread receives all of them.
-    // Contains one __syncthreads; the caller guarantees another barrier before the next call.
+    // Contains one instance barrier; the caller guarantees another barrier before the next call.
     template <int V>
     __device__ __forceinline__ void block_reduce(float (&v)[32], float (&out)[V]) {
         warp_transpose_reduce32(v, lane);
         part()[lane * SH::NW + warp] = v[0];
-        __syncthreads();
+        gbar();
 #pragma unroll
         for (int i = 0; i < V; ++i) {
             float s = 0.f;
@@ -186,11 +199,11 @@ __device__ __noinline__ void lat_eval_fwd(LatCtx<SH>& c, const KParams& p, const
 #pragma unroll
         for (int a = 0; a < NS; ++a) red[SL_G + a] = c.wg2[a] * ag;
     }
-    __syncthreads();  // a1 visible (also separates this evaluation's exchange from the previous one's reads)
+    c.gbar();  // a1 visible (also separates this evaluation's exchange from the previous one's reads)
     const float a2 = tanh_acc(c.matvec(c.W2T(), c.vec(0)) + c.b2);
     red[SL_H] = c.w3 * a2;
     c.vec(1)[c.k] = fmaf(-a2, a2, 1.f) * c.w3;
-    __syncthreads();  // delta2 visible
+    c.gbar();  // delta2 visible
     const float g1 = c.matvec(c.W2(), c.vec(1));
     const float d1 = fmaf(-a1, a1, 1.f) * g1;
 #pragma unroll
@@ -275,7 +288,7 @@ __device__ __noinline__ void lat_eval_vjp(LatCtx<SH>& c, const KParams& p, const
 #pragma unroll
             for (int a = 0; a < NS; ++a) red[SL_G + a] = c.wg2[a] * ag;
         }
-        __syncthreads();  // the previous evaluation's exchange has been read by everyone
+        c.gbar();  // the previous evaluation's exchange has been read by everyone
         float tot[NV1 > 0 ? NV1 : 1];
         c.template block_reduce<(NV1 > 0 ? NV1 : 1)>(red, tot);
         lat_make_S<NS>(p, tot, S);
@@ -303,14 +316,14 @@ __device__ __noinline__ void lat_eval_vjp(LatCtx<SH>& c, const KParams& p, const
     const float da1 = s1 * dotv<NS>(c.w1, w, 0.f);
     c.vec(0)[c.k] = a1;
     c.vec(1)[c.k] = da1;
-    __syncthreads();
+    c.gbar();
     float z2, dz2;
     c.matvec2(c.W2T(), c.vec(0), c.vec(1), z2, dz2);
     const float a2 = tanh_acc(z2 + c.b2);
     const float s2 = fmaf(-a2, a2, 1.f);
     c.vec(2)[c.k] = s2 * c.w3;
     c.vec(3)[c.k] = -2.f * a2 * (s2 * dz2) * c.w3;
-    __syncthreads();
+    c.gbar();
     float g1, dg1;
     c.matvec2(c.W2(), c.vec(2), c.vec(3), g1, dg1);
     const float t = fmaf(-2.f * a1 * da1, g1, s1 * dg1);
@@ -385,7 +398,7 @@ __device__ __noinline__ void lat_eval_vjp(LatCtx<SH>& c, const KParams& p, const
             red[i] = c.wr1[i] * zb;
             if constexpr (SH::HAS_GNET) red[i] = fmaf(c.wg1[i], zg, red[i]);
         }
-        __syncthreads();  // everyone has read the previous exchange
+        c.gbar();  // everyone has read the previous exchange
         float tot3[NS];
         c.template block_reduce<NS>(red, tot3);
 #pragma unroll
@@ -398,10 +411,10 @@ __device__ __noinline__ void lat_eval_vjp(LatCtx<SH>& c, const KParams& p, const
 }
 
 // ---------------------------------------------------------------------------------------
-// the kernel: grid = B instances, block = HID threads
+// the kernel: grid = ceil(B / ng) CTAs of up to NI instances (ng in use), HID threads per instance
 // ---------------------------------------------------------------------------------------
 template <int MK, int NS, int HID>
-__global__ void __launch_bounds__(HID, 1) phnn_lat_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(LatShape<MK, NS, HID>::THREADS, PHNN_LAT_MINBLOCKS) phnn_lat_kernel(const __grid_constant__ KParams p) {
     using SH = LatShape<MK, NS, HID>;
     using FS = typename SH::FS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);
@@ -418,10 +431,11 @@ __global__ void __launch_bounds__(HID, 1) phnn_lat_kernel(const __grid_constant_
         bulk_g2s(phnn_smem + 128 + HID * HID * 4, p.wbig + HID * HID, HID * HID * 4u, &bars[0]);
     }
     LatCtx<SH> c;
-    c.k = threadIdx.x;
+    c.k = threadIdx.x % HID;
+    c.inst = threadIdx.x / HID;
     c.lane = threadIdx.x & 31;
-    c.warp = threadIdx.x >> 5;
-    c.store = (threadIdx.x == 0);
+    c.warp = c.k >> 5;
+    c.store = (c.k == 0);
     const float* ws = p.wsmall;
 #pragma unroll
     for (int i = 0; i < NS; ++i) c.w1[i] = ws[FS::O_W1 + c.k * NS + i];
@@ -444,8 +458,13 @@ __global__ void __launch_bounds__(HID, 1) phnn_lat_kernel(const __grid_constant_
         for (int a = 0; a < NS; ++a) c.wg2[a] = ws[FS::O_WG2 + a * HID + c.k];
     }
     mbar_wait(&bars[0], 0);
+    // p.ng = instance slots in use per CTA (the host spreads a small batch over the SMs before it stacks instances
+    // on one: co-resident instances share the shared-memory pipe and run ~2x slower each); unused slots and slots
+    // past the end of the batch leave here (every later barrier is per instance)
+    const long long my_instance = (long long)blockIdx.x * p.ng + c.inst;
+    if (c.inst >= p.ng || my_instance >= p.B) return;
     int n_outer = (p.mode == MODE_SOLVE) ? p.iters : 1;
-    StaticSched sched{(long long)blockIdx.x, n_outer, 0};
+    StaticSched sched{my_instance, n_outer, 0};
     run_job(c, p, sched, 0);
 }
 
