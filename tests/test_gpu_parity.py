@@ -424,15 +424,47 @@ def test_lat_matches_batched_kernel(lat_env, env):
         assert np.abs(outs[0][0].cpu().numpy() - outs[1][0].cpu().numpy()).max() < 0.02 * lr + 1e-5
 
 
+@pytest.mark.parametrize("name,B", [("cartpole_h128", 300), ("canonical", 450), ("pendulum", 1500)])
+def test_lat_stacked_instances_vs_oracle(lat_env, name, B):
+    """batches between one and several instances per SM: the latency kernel stacks 2..8 instances on a CTA (shared
+    weights, per-instance barriers, ragged last CTA); cost, dJ/dU and three Adam steps against the CPU oracle"""
+    from oracle.phnn_oracle import OracleModel
+    ops, get_lat = lat_env
+    z, sd, pk = get_lat(name)
+    assert B <= pk.get_option("latency_max_batch")
+    M = OracleModel(sd, KINDS[name])
+    n = z["mpc_x0"].shape[1]
+    H = 12
+    g = torch.Generator().manual_seed(B)
+    scale = torch.tensor([1.0, 0.3, 0.5, 0.5][:n]) if n == 4 else torch.tensor([1.5, 1.0])
+    x0 = ((torch.rand(B, n, generator=g) * 2 - 1) * scale).numpy()
+    U0 = ((torch.rand(B, H, 1, generator=g) * 2 - 1) * 2).numpy()
+    ca = cost_args(z)
+    Q, R, xt = [t.numpy() for t in ca[:3]]
+    lo, hi = ca[4], ca[5]
+    C = M.cost_struct(Q, R, xt, lo, hi)
+    dt, lr = float(z["mpc_dt"]), float(z["mpc_lr"])
+    Jo, go = M.cost_grad(C, x0, U0, dt, "rk4")
+    cost, gg, _ = ops.cost_grad(pk.handle, cu(x0), cu(U0), dt, 1, *ca, True, False)
+    assert rel_err(cost.cpu().numpy(), Jo) < HORIZON_TOL
+    assert rel_err(gg.cpu().numpy(), go) < HORIZON_TOL
+    Uo, histo, _ = M.mpc_solve(C, x0, U0, dt, "rk4", lr=lr, iters=3)
+    U, hist, _ = ops.mpc_solve(pk.handle, cu(x0), cu(U0), dt, 1, *ca, lr, 0.9, 0.999, 1e-8, 3, 0, True)
+    assert rel_err(hist.cpu().numpy(), histo) < HORIZON_TOL
+    assert np.abs(U.cpu().numpy() - Uo).max() < 0.02 * lr + 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE cfg5 horizons and full-size properties
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("H", [100, 200])
-def test_tc_long_horizons_vs_oracle(tc_env, H):
-    """cfg5 horizons (RK4, h=256) on a 128-instance sub-sample against the CPU oracle: cost, dJ/dU, two Adam steps."""
+def test_tc_long_horizons_vs_oracle(tc_env, H, mode):
+    """cfg5 horizons (RK4, h=256) on a 128-instance sub-sample against the CPU oracle: cost, dJ/dU, two Adam steps;
+    both FP32-level tensor schemes (2: TF32 + BF16 correction product, the default; 3: 3xTF32)."""
     from oracle.phnn_oracle import OracleModel
     ops, get_tc = tc_env
-    z, sd, pk = get_tc("cartpole_h256", 3)
+    z, sd, pk = get_tc("cartpole_h256", mode)
     M = OracleModel(sd, "phnn")
     B = 128
     g = torch.Generator().manual_seed(H)
@@ -459,7 +491,7 @@ def test_full_size_properties_cfg4(tc_env):
     permutation invariance (bit for bit: instances are independent and every reduction order is fixed), bounded
     controls, monotone best cost, zero-iteration solve."""
     ops, get_tc = tc_env
-    z, sd, pk = get_tc("cartpole_h256", 3)
+    z, sd, pk = get_tc("cartpole_h256", 2)
     B, H, iters = 65536, 8, 3
     g = torch.Generator().manual_seed(4)
     x0 = ((torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])).cuda()
