@@ -254,6 +254,10 @@ __device__ __forceinline__ float2 tanh_tc2(float2 x) {
 #ifndef PHNN_TC_MMA_SLEEP
 #define PHNN_TC_MMA_SLEEP 128
 #endif
+// blocks by which the R_net work trails the hand-off of the producing loops (0: same block)
+#ifndef PHNN_TC_RSKEW
+#define PHNN_TC_RSKEW 2
+#endif
 #ifndef PHNN_TC_RFENCE
 #define PHNN_TC_RFENCE 4
 #endif
@@ -486,9 +490,17 @@ __device__ __forceinline__ void tc_phase_a1(TcCtx<SH>& c, const float (&z)[4], c
             if (c.tape) *c.tape4(1, kb, q) = make_float4(av[q][0], av[q][1], av[q][2], av[q][3]);  // read back in phase C
         }
         const int slot = c.a_begin();
-c.a_put_block(slot, av);
+        c.a_put_block(slot, av);
         c.a_end(slot);
-        if constexpr (SH::HAS_R) tc_rfwd_pairs<0, SH::PP / 2>(c, kb, y, Sp2);
+        // R_net pairs run PHNN_TC_RSKEW blocks behind: that many blocks (+1) of them are left after the last hand-off and
+        // cover the tail of the MMA before the wait for its accumulator
+        if constexpr (SH::HAS_R) {
+            if (kb >= PHNN_TC_RSKEW) tc_rfwd_pairs<0, SH::PP / 2>(c, kb - PHNN_TC_RSKEW, y, Sp2);
+        }
+    }
+    if constexpr (SH::HAS_R) {
+#pragma unroll
+        for (int kb = SH::NKB - PHNN_TC_RSKEW; kb < SH::NKB; ++kb) tc_rfwd_pairs<0, SH::PP / 2>(c, kb, y, Sp2);
     }
 }
 
@@ -552,11 +564,17 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
                 if (c.tape) __stcs(c.tape4(0, jb, q), make_float4(a2v[0], a2v[1], a2v[2], a2v[3]));
             }
             const int slot = c.a_begin();
-c.a_put_block(slot, dv);
+            c.a_put_block(slot, dv);
             c.a_end(slot);
             // the rest of the R_net forward pairs rides here: this loop otherwise waits for the MMA
-            if constexpr (SH::HAS_R) tc_rfwd_pairs<SH::PP / 2, SH::PP>(c, jb, y, Sp2);
+            if constexpr (SH::HAS_R) {
+                if (jb >= PHNN_TC_RSKEW) tc_rfwd_pairs<SH::PP / 2, SH::PP>(c, jb - PHNN_TC_RSKEW, y, Sp2);
+            }
         });
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int jb = NKB - PHNN_TC_RSKEW; jb < NKB; ++jb) tc_rfwd_pairs<SH::PP / 2, SH::PP>(c, jb, y, Sp2);
+        }
         X[12] = Hp2.x + Hp2.y;
     }
     TCP_MARK(c, 2);
@@ -675,6 +693,16 @@ __device__ __forceinline__ void tc_rback_pair(const TcCtx<SH>& c, int P, const f
     pair_scatter(u01, u23, mul2(rb, one_minus_sq(r1)), X2);
 }
 
+// pairs [I0, I1) of this thread's PP in K-block kb
+template <int I0, int I1, class SH>
+__device__ __forceinline__ void tc_rback_pairs(const TcCtx<SH>& c, int kb, const float (&y)[4], const float (&Rb)[12], float2 (&X2)[4]) {
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+        tc_rback_pair(c, tc_pair(c, kb, i), y, Rb, X2);
+        if ((i - I0) % 2 == 1) sched_fence();
+    }
+}
+
 template <class SH>
 __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u,
                                          const float (&v)[4], float (&xbar)[4], float& ubar) {
@@ -768,15 +796,15 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
                 }
             }
             const int slot = c.a_begin();
-c.a_put_block(slot, av);
+            c.a_put_block(slot, av);
             c.a_end(slot);
             if constexpr (SH::HAS_R) {
-#pragma unroll
-                for (int i = 0; i < SH::PP / 2; ++i) {
-                    tc_rback_pair(c, tc_pair(c, kb, i), y, Rb, X2);
-                    if (i % 2 == 1) sched_fence();
-                }
+                if (kb >= PHNN_TC_RSKEW) tc_rback_pairs<0, SH::PP / 2>(c, kb - PHNN_TC_RSKEW, y, Rb, X2);
             }
+        }
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc_rback_pairs<0, SH::PP / 2>(c, kb, y, Rb, X2);
         }
     }
     TCP_MARK(c, 6);
@@ -804,16 +832,16 @@ c.a_put_block(slot, av);
                 }
             }
             const int slot = c.a_begin();
-c.a_put_block(slot, ev);
+            c.a_put_block(slot, ev);
             c.a_end(slot);
             if constexpr (SH::HAS_R) {
-#pragma unroll
-                for (int i = SH::PP / 2; i < SH::PP; ++i) {
-                    tc_rback_pair(c, tc_pair(c, jb, i), y, Rb, X2);
-                    if ((i - SH::PP / 2) % 2 == 1) sched_fence();
-                }
+                if (jb >= PHNN_TC_RSKEW) tc_rback_pairs<SH::PP / 2, SH::PP>(c, jb - PHNN_TC_RSKEW, y, Rb, X2);
             }
         });
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int jb = NKB - PHNN_TC_RSKEW; jb < NKB; ++jb) tc_rback_pairs<SH::PP / 2, SH::PP>(c, jb, y, Rb, X2);
+        }
     }
     TCP_MARK(c, 8);
     // ---- C4: the dg1 half of xbar_H ----
