@@ -82,8 +82,9 @@ int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
  *                      accuracy, 1.5x the tensor work); 1: plain TF32 (looser).
  *   "tensor_min_batch" smallest B routed to the tcgen05 kernel (default 1: it beats the FP32-FMA kernel
  *                      at every batch size; small batches go to the latency kernel first).
- *   "latency_max_batch" largest B routed to the one-CTA-per-instance latency kernel (default 6-64 x SM
- *                      count by measured crossover, where built: hidden width <= 128; 0 disables it).                    */
+ *   "latency_max_batch" largest B routed to the latency kernel (one thread per hidden unit, up to 8 instances
+ *                      per CTA; default 8-96 x SM count by measured crossover, where built: hidden width <= 128;
+ *                      0 disables it).                                                                                   */
 int phnn_pack_set_option(phnn_pack *pack, const char *key, long value);
 long phnn_pack_get_option(const phnn_pack *pack, const char *key);
 
@@ -104,7 +105,10 @@ int phnn_vjp(const phnn_pack *pack, const float *x, const float *u, const float 
 int phnn_rollout(const phnn_pack *pack, const float *x0, const float *U, float *traj, float *energies,
                  long B, int T, double dt, int integrator, int energy_mode, void *stream);
 
-/* Bytes of scratch phnn_cost_grad / phnn_mpc_solve need for (B, T).                            */
+/* Bytes of scratch phnn_cost_grad / phnn_mpc_solve need for (B, T) under the pack's current options: stage-state
+ * checkpoints, Adam moments and best controls per instance; for a batch routed to the tcgen05 kernel also its
+ * scheduler words and the activation tape (one region of T*S*3*h*128*4 bytes per SM, S = 4 for RK4).  The
+ * contents need not be preserved between calls.                                                 */
 size_t phnn_workspace_bytes(const phnn_pack *pack, long B, int T, int integrator);
 
 /* cost[B] and dJdU[B,T,m] (NULL: cost only) of the horizon cost at U[B,T,m]

@@ -538,3 +538,41 @@ def test_rollout_linearity_in_time_cfg2_size():
     assert torch.equal(tr[:, :51], tra) and torch.equal(tr[:, 50:], trb)
     assert torch.equal(en1[:, 1:], en2[:, :-1]) and torch.equal(en1[:, 0], en2[:, 0])
     assert torch.isfinite(tr).all()
+
+
+def test_workspace_contract(tc_env):
+    """phnn_workspace_bytes follows the documented layout (per-instance part + scheduler words + one tape region per
+    SM for the tcgen05 route), shrinks to the per-instance part when the tcgen05 route is off, and a workspace that is
+    too small is refused with PHNN_E_WORKSPACE instead of being overrun."""
+    import ctypes
+    from phnn_mpc_b200 import _lib
+    ops, get_tc = tc_env
+    z, sd, pk = get_tc("cartpole_h256", 2)
+    L = _lib.lib()
+    L.phnn_workspace_bytes.restype = ctypes.c_size_t
+    L.phnn_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int]
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, T, h, n = 1000, 7, 256, 4
+    for integ, S in ((0, 1), (1, 4)):
+        tiles = (B + 127) // 128
+        per_tile = 128 * (T * S * n + 3 * T + 1 + 16 * T * S) * 4
+        sched = -(-(tiles * per_tile + 4 * (tiles + 4)) // 128) * 128
+        tape = min(tiles, sms) * T * S * 3 * h * 128 * 4
+        assert L.phnn_workspace_bytes(ctypes.c_void_p(pk.handle), B, T, integ) == sched + tape
+    pk.set_option("tensor_mode", 0)
+    try:
+        assert L.phnn_workspace_bytes(ctypes.c_void_p(pk.handle), B, T, 1) == -(-(8 * 128 * (T * 4 * n + 3 * T + 1 + 16 * T * 4) * 4 + 4 * 12) // 128) * 128
+    finally:
+        pk.set_option("tensor_mode", 2)
+    x0 = torch.zeros(B, n, device="cuda")
+    U = torch.zeros(B, T, 1, device="cuda")
+    ca = cost_args(z)
+    cd = ops._Cost(*ca)
+    small = torch.empty(1024, device="cuda")
+    cost = torch.empty(B, device="cuda")
+    g = torch.empty_like(U)
+    rc = L.phnn_cost_grad(ctypes.c_void_p(pk.handle), ctypes.byref(cd.desc), ctypes.c_void_p(x0.data_ptr()),
+                          ctypes.c_void_p(U.data_ptr()), ctypes.c_void_p(cost.data_ptr()), ctypes.c_void_p(g.data_ptr()), None,
+                          B, T, ctypes.c_double(0.02), 1, ctypes.c_void_p(small.data_ptr()), small.numel() * 4, None)
+    assert rc == _lib.E_WORKSPACE
+    assert b"workspace too small" in L.phnn_last_error()
