@@ -258,6 +258,10 @@ __device__ __forceinline__ float2 tanh_tc2(float2 x) {
 #ifndef PHNN_TC_RSKEW
 #define PHNN_TC_RSKEW 2
 #endif
+// L2 prefetch distance of the tape, in K-block steps of the adjoint loops
+#ifndef PHNN_TC_PF_AHEAD
+#define PHNN_TC_PF_AHEAD 3
+#endif
 #ifndef PHNN_TC_RFENCE
 #define PHNN_TC_RFENCE 4
 #endif
@@ -580,15 +584,16 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
     TCP_MARK(c, 2);
     // ---- phase C: dH = W1^T (s1 * g1) ----
     {
-        const uint32_t tacc = c.acc_wait();
-        TCP_MARK(c, 3);
         float2 G2[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) G2[i] = make_float2(0.f, 0.f);
         if (c.tape) {
-            // a1 comes back from the tape (written by this thread in phase A, still in L2)
+            // a1 comes back from the tape (written by this thread in phase A, still in L2); the first block is
+            // requested before the wait for the accumulator
             float4 an[SH::CQ];
             c.tape_load<false>(1, 0, an);
+            const uint32_t tacc = c.acc_wait();
+            TCP_MARK(c, 3);
             for_acc_blocks<NKB, SH::UP>(tacc, [&](int kb, const uint32_t (&gr)[SH::UP]) {
                 float4 ac[SH::CQ];
 #pragma unroll
@@ -608,6 +613,8 @@ __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, cons
                 }
             });
         } else {
+            const uint32_t tacc = c.acc_wait();
+            TCP_MARK(c, 3);
             for_acc_blocks<NKB, SH::UP>(tacc, [&](int kb, const uint32_t (&gr)[SH::UP]) {
 #pragma unroll
                 for (int i = 0; i < SH::PP; ++i) {
@@ -712,6 +719,10 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     float z[4], w[4], G4[4], sv[4], Rb[12];
     Canon cq = {};
     float pb[2] = {0.f, 0.f}, pdb[2] = {0.f, 0.f};
+    // first tape blocks of the da1 loop, requested before the per-instance algebra below
+    float4 an[SH::CQ], gn[SH::CQ];
+    c.tape_load<false>(1, 0, an);
+    c.tape_load<true>(2, 0, gn);
     // grad H of the forward evaluation at this stage state (ld.cg: written by the partner thread)
 #pragma unroll
     for (int i = 0; i < 4; ++i) G4[i] = __ldcg(c.sck + ((size_t)c.ev * 16 + 10 + i) * 128 + c.row);
@@ -769,9 +780,6 @@ __device__ __forceinline__ void tc_eval_vjp(TcCtx<SH>& c, const KParams& p, cons
     // ---- A3: da1 = s1 * (W1 w) -> product 1 (dz2 = W2 da1), with the g1 half of xbar_H (sdot1 * g1) and part
     //      of the R_net chain in the same loop (the loop runs at the pace of the MMA) ----
     {
-        float4 an[SH::CQ], gn[SH::CQ];
-        c.tape_load<false>(1, 0, an);
-        c.tape_load<true>(2, 0, gn);
 #pragma unroll 1
         for (int kb = 0; kb < NKB; ++kb) {
             float4 ac[SH::CQ], gc[SH::CQ];
@@ -1161,7 +1169,7 @@ __global__ void __launch_bounds__(TcShape<MK, NS, HID>::THREADS, 1) phnn_tc_kern
                         if (qi >= 0) {
                             // pull the tape blocks the element threads will read PF_AHEAD K-block steps from now
                             // into L2 (they were written a whole sweep ago, so they come from HBM)
-                            constexpr int PF_AHEAD = 3;
+                            constexpr int PF_AHEAD = PHNN_TC_PF_AHEAD;
                             int step = (int)(qi & 1) * SH::NKB + kb + PF_AHEAD;
                             long long te = (long long)E - 1 - (qi >> 1);
                             if (step >= 2 * SH::NKB) { step -= 2 * SH::NKB; --te; }
