@@ -576,3 +576,27 @@ def test_workspace_contract(tc_env):
                           B, T, ctypes.c_double(0.02), 1, ctypes.c_void_p(small.data_ptr()), small.numel() * 4, None)
     assert rc == _lib.E_WORKSPACE
     assert b"workspace too small" in L.phnn_last_error()
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_tc_wide_states_and_saturated_units(tc_env, mode):
+    """the tensor-core schemes at the edge of their operand range: states over the range of the reference's training
+    data (|x| up to ~20: most tanh units saturate, so a1 is +-1 and delta2 / s1 are tiny) - forward against the golden
+    values recorded from the reference, cost and dJ/dU of a short horizon from those states against the CPU oracle"""
+    from oracle.phnn_oracle import OracleModel
+    ops, get_tc = tc_env
+    for name in ("cartpole_h128", "cartpole_h256"):
+        z, sd, pk = get_tc(name, mode)
+        dx, H = ops.forward(pk.handle, cu(z["wide_x"]), cu(z["rand_u"][:16]))
+        assert rel_err(dx.cpu().numpy(), z["wide_dx"]) < STEP_TOL
+        assert rel_err(H.cpu().numpy(), z["wide_H"]) < STEP_TOL
+        M = OracleModel(sd, "phnn")
+        x0 = np.ascontiguousarray(z["wide_x"], np.float32)
+        B, T = x0.shape[0], 6
+        U0 = np.random.default_rng(5).uniform(-3, 3, size=(B, T, 1)).astype(np.float32)
+        ca = cost_args(z)
+        C = M.cost_struct(ca[0].numpy(), ca[1].numpy(), ca[2].numpy(), ca[4], ca[5])
+        Jo, go = M.cost_grad(C, x0, U0, 0.02, "rk4")
+        cost, gg, _ = ops.cost_grad(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, True, False)
+        assert rel_err(cost.cpu().numpy(), Jo) < HORIZON_TOL
+        assert rel_err(gg.cpu().numpy(), go) < HORIZON_TOL
