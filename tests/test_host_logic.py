@@ -186,3 +186,22 @@ def test_packed_weight_file_roundtrip_and_reference_checkpoint_layouts(tmp_path)
     with pytest.raises(ValueError):
         (tmp_path / "bad.bin").write_bytes(b"notapack" + b"\0" * 64)
         weights_io.load_packed(str(tmp_path / "bad.bin"))
+
+
+def test_bench_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) prints ONE JSON line with the keys the
+    driver reads; no GPU, no kernel of ours on that path."""
+    import json
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "small"], capture_output=True, text=True, timeout=600, cwd=repo)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "cartpole_mpc_solves_per_s" and d["unit"] == "solves/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d.get("gpu_launches", 0) == 0
