@@ -224,6 +224,31 @@ static bool shape_small(int mk, int n, int h, const phnn_model_desc* d, std::vec
     return false;
 }
 
+// The kernels of one model shape need more dynamic shared memory than the 48 KB default: raise the limit once per
+// (kernel, device) when a pack for that shape is created on the device, not on every launch.
+static cudaError_t set_smem_limits(int mk, int n, int h) {
+    cudaError_t e = cudaSuccess;
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                 (int)Shape<MK, NS, HID>::smem_bytes(Shape<MK, NS, HID>::MAX_NG));
+    PHNN_SHAPES(X)
+#undef X
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_tc_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                 (int)TcShape<MK, NS, HID>::SMEM_BYTES);
+    PHNN_TC_SHAPES(X)
+#undef X
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_lat_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                 (int)LatShape<MK, NS, HID>::SMEM_BYTES);
+    PHNN_LAT_SHAPES(X)
+#undef X
+    return e;
+}
+
 extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack** out) {
     if (!d || !out) return fail(PHNN_E_ARG, "phnn_pack_create: null argument");
     *out = nullptr;
@@ -265,6 +290,7 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
     cudaError_t e = cudaGetDevice(&prev);
     if (e == cudaSuccess) e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pk->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = set_smem_limits(mk, d->n, d->h);
     if (e == cudaSuccess) e = cudaMalloc(&pk->d_small, small.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&pk->d_big, big.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(pk->d_small, small.data(), small.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -357,9 +383,12 @@ extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) 
     return fail(PHNN_E_ARG, "unknown option %s", key);
 }
 
-// debug: device buffer (32 x int64) that PHNN_TC_PROFILE builds fill with per-phase cycle counts
+#ifdef PHNN_TC_PROFILE
+// profiling builds only (tools/gpu_tc_phases.py): device buffer (34 x int64) the instrumented kernel fills with
+// per-phase cycle counts.  The production library has no such hook and no global mutable state.
 static long long* g_dbg = nullptr;
 extern "C" void phnn_debug_set_buffer(void* p) { g_dbg = (long long*)p; }
+#endif
 
 extern "C" long phnn_pack_get_option(const phnn_pack* pk, const char* key) {
     if (!pk || !key) return -1;
@@ -387,8 +416,7 @@ static int launch_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
     P.ng = (int)ng;
     const long long grid = (groups + ng - 1) / ng;
     const size_t smem = SH::smem_bytes((int)ng);
-    auto kern = phnn_kernel<SH::MK, SH::NS, SH::HID>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = phnn_kernel<SH::MK, SH::NS, SH::HID>;  // dynamic shared-memory limit: set once in phnn_pack_create
     const int threads = ((int)ng * SH::NWG + 1) * 32;
     kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
@@ -398,7 +426,6 @@ static int launch_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
 template <class SH>
 static int launch_lat_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
     auto kern = phnn_lat_kernel<SH::MK, SH::NS, SH::HID>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
     // instances per CTA: one per SM first, stacked (up to NI, sharing the weights in shared memory) only when the batch
     // exceeds the SM count
     long long per = (P.B + pk->num_sms - 1) / pk->num_sms;
@@ -434,16 +461,23 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     static_assert((3 * SH::HID * 128 * 4) % 65536 == 0, "tape prefetch granularity");
     const long long tiles = (P.B + SH::TM - 1) / SH::TM;
     auto kern = phnn_tc_kernel<SH::MK, SH::NS, SH::HID>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM_BYTES));
     P.tc_split = pk->tc_mode;  // 1 plain TF32, 2 TF32 + BF16 correction product, 3 3xTF32
     if (pk->tc_mode == 2) P.wtc = pk->d_wtc2;
     P.ng = 1;
+#ifdef PHNN_TC_PROFILE
     P.dbg = g_dbg;
+#else
+    P.dbg = nullptr;
+#endif
     P.tiles = tiles;
     P.sched = nullptr;
     P.tape = nullptr;
     long long grid = tiles;
-    static const bool no_steal = getenv("PHNN_NO_STEAL") != nullptr;  // experiment switch
+#ifdef PHNN_TC_PROFILE
+    static const bool no_steal = getenv("PHNN_NO_STEAL") != nullptr;  // experiment switch (profiling builds only)
+#else
+    constexpr bool no_steal = false;
+#endif
     const bool adjoint = (P.mode == MODE_SOLVE && P.iters > 0) || (P.mode == MODE_COSTGRAD && P.want_grad);
     if (adjoint) {
         // the forward sweep tapes its activations into a per-CTA region: at most one CTA per SM, each running

@@ -109,10 +109,13 @@ def _forward_setup(ctx, inputs, output):
     pack, x, u = inputs
     ctx.pack = pack
     ctx.save_for_backward(x, u)
+    # H carries no autograd formula here (the weights are not op inputs and dH/dx is not exported): differentiating
+    # through it raises instead of silently contributing nothing
+    ctx.mark_non_differentiable(output[1])
 
 
 def _forward_backward(ctx, grad_dx, grad_H):
-    # First-order only; H is returned detached by the modules, so grad_H is not propagated.
+    # First-order in (x, u) through dx only; parameters receive no gradient from this op.
     x, u = ctx.saved_tensors
     xb, ub = vjp(ctx.pack, x, u, grad_dx.contiguous())
     return None, xb, ub

@@ -93,7 +93,9 @@ class PackedModel:
             raise ValueError("unknown model kind %r" % (kind,))
         self.kind, self.n, self.m, self.h = kind, d.n, d.m, d.h
         handle = ctypes.c_void_p()
-        _lib.check(L.phnn_pack_create(ctypes.byref(d), self.device.index or 0, ctypes.byref(handle)),
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        _lib.check(L.phnn_pack_create(ctypes.byref(d), self.device.index, ctypes.byref(handle)),
                    "phnn_pack_create")
         self.handle = handle.value
         self._fin = weakref.finalize(self, L.phnn_pack_destroy, ctypes.c_void_p(self.handle))
@@ -122,12 +124,29 @@ class PackedModel:
 _cache = weakref.WeakKeyDictionary()
 
 
+def _fingerprint(t):
+    """cheap content fingerprint: catches in-place writes through ``param.data`` (``p.data.copy_``, EMA code, older
+    optimizers), which bump neither ``_version`` nor ``data_ptr``.  The models here are < 0.3 MB of weights."""
+    d = t.detach()
+    if d.numel() == 0:
+        return (0.0, 0.0)
+    d = d.double()
+    return (float(d.sum()), float(d.abs().sum()))
+
+
+def invalidate(module):
+    """drop the cached device image of `module` (the next pack_of repacks)"""
+    _cache.pop(module, None)
+
+
 def pack_of(module, device=None):
-    """Packed image of an nn.Module, rebuilt when any parameter/buffer changed (tracked by the
-    tensors' _version counters and data pointers)."""
+    """Packed image of an nn.Module, rebuilt when any parameter/buffer changed (tracked by the tensors' _version
+    counters, data pointers and a content fingerprint)."""
     tensors = list(module.state_dict(keep_vars=True).items())
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    key = (str(dev),) + tuple((k, t._version, t.data_ptr()) for k, t in tensors)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    key = (str(dev),) + tuple((k, t._version, t.data_ptr()) + _fingerprint(t) for k, t in tensors)
     hit = _cache.get(module)
     if hit is not None and hit[0] == key:
         return hit[1]

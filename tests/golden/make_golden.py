@@ -341,8 +341,38 @@ def gen_closed_loop():
     print("closed loop done; u[0] =", out["cl_u"][0], "canon u[0] =", outc["cl_u"][0])
 
 
+def gen_cfg4_shape():
+    """BASELINE cfg4 at a reference-runnable size: the cfg4 model (cartpole_h256.npz weights), the first 64 of the
+    benchmark's own instances (bench.make_inputs(., 'phnn', 7)), H=50, RK4, 20 Adam iterations, cold start --
+    exactly the job bench.py times per instance (src/integrators.py:192-258 + src/mpc_controller.py:143-209 composed
+    as in SURVEY.md section 8c).  About two minutes of reference CPU time."""
+    z = np.load(os.path.join(HERE, "cartpole_h256.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model = pHNN(wide_cfg(256))
+    model.load_state_dict(sd)
+    model.eval()
+    cfg = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    mpc = cfg["mpc"]
+    g = torch.Generator().manual_seed(7)
+    B, Hh, iters = 64, 50, 20
+    x0 = ((torch.rand(65536, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])).float()[:B]
+    Q = torch.diag(torch.tensor(mpc["Q_diag"]))
+    R = torch.tensor([[mpc["R_diag"][0]]])
+    xt = torch.tensor(mpc["x_target"])
+    dt = cfg["cartpole"]["dt"]
+    res = composition_solve(model, x0, torch.zeros(B, Hh, 1), dt, "rk4", Q, R, xt, mpc["u_min"], mpc["u_max"],
+                            mpc["learning_rate"], iters, "last")
+    out = {"x0": x0.numpy(), "H": np.int32(Hh), "iters": np.int32(iters), "dt": np.float32(dt),
+           "lr": np.float32(mpc["learning_rate"]), "Q": Q.numpy(), "R": R.numpy(), "xt": xt.numpy(),
+           "bounds": np.array([mpc["u_min"], mpc["u_max"]], np.float32)}
+    for k, val in res.items():
+        out["rk4_" + k] = val
+    np.savez(os.path.join(HERE, "cfg4_shape.npz"), **out)
+    print("cfg4_shape done; cost[0] first/last =", res["hist"][0, 0], res["hist"][-1, 0])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop"]
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape"]
     if "pendulum" in which:
         gen_pendulum()
     if "h128" in which:
@@ -353,3 +383,5 @@ if __name__ == "__main__":
         gen_canonical()
     if "closed_loop" in which:
         gen_closed_loop()
+    if "cfg4_shape" in which:
+        gen_cfg4_shape()

@@ -139,11 +139,16 @@ rank, ws = dist.get_rank(), dist.get_world_size()
 B = 37
 x0 = torch.arange(B * 4, dtype=torch.float32).reshape(B, 4)
 U0 = torch.arange(B * 5, dtype=torch.float32).reshape(B, 5, 1)
+ITERS = 18                 # equals the size of rank 1's shard (37 = 19 + 18): the old shape test gathered cost_hist on
+                           # one rank only and along the wrong axis (ADVICE r1)
 def fake_solve(x, U):      # stands in for BatchedMPC.solve: any per-instance map
-    return {"U": U * 2 + x[:, :1, None], "u0": (U * 2 + x[:, :1, None])[:, 0], "best_cost": x.sum(1), "cost_hist": None}
+    hist = torch.arange(ITERS, dtype=torch.float32)[:, None] * 100 + x[:, 0][None, :]
+    return {"U": U * 2 + x[:, :1, None], "u0": (U * 2 + x[:, :1, None])[:, 0], "best_cost": x.sum(1), "cost_hist": hist}
 out = sharded_solve(fake_solve, x0, U0)
 ref = fake_solve(x0, U0)
-ok = all(torch.equal(out[k], ref[k]) for k in ("U", "u0", "best_cost"))
+ok = all(torch.equal(out[k], ref[k]) for k in ("U", "u0", "best_cost", "cost_hist")) and out["cost_hist"].shape == (ITERS, B)
+out2 = sharded_solve(lambda x, U: dict(fake_solve(x, U), cost_hist=None), x0, U0)
+ok = ok and "cost_hist" not in out2 and torch.equal(out2["U"], ref["U"])
 print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
@@ -189,19 +194,32 @@ def test_packed_weight_file_roundtrip_and_reference_checkpoint_layouts(tmp_path)
 
 
 def test_bench_reference_arm_line_contract():
-    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) prints ONE JSON line with the keys the
-    driver reads; no GPU, no kernel of ours on that path."""
+    """`bench.py --impl reference` (the CPU arm: the unmodified reference PyTorch path staged under oracle/_ref, on the
+    host cores) prints ONE JSON line with the keys the driver reads and the SAME config / steps / warmup as our arm
+    would report; no GPU, no kernel of ours on that path."""
     import json
     import subprocess
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--workload", "small"], capture_output=True, text=True, timeout=600, cwd=repo)
+    sys.path.insert(0, repo)
+    from oracle import fetch_ref
+    if os.path.isdir(fetch_ref.DEFAULT_REF):
+        fetch_ref.fetch(quiet=True)
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--workload", "small", "--ref-budget", "12"], capture_output=True, text=True, timeout=600, cwd=repo)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cartpole_mpc_solves_per_s" and d["unit"] == "solves/s"
-    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1
+    import bench
+    cfg, _, _ = bench.workload_config("small", list(bench.WORKLOADS["small"]), 1)
+    assert d["config"] == cfg                      # what our arm prints for the same command line
+    if fetch_ref.available():
+        assert d["cpu_baseline"]["kind"] == "reference-pytorch" and d["cpu_baseline"]["torch_threads"] >= 1
+        assert "oracle/_ref" in d["cpu_baseline"]["sample"]
+    else:
+        assert d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d.get("gpu_launches", 0) == 0

@@ -117,3 +117,22 @@ def test_controller_cfg3():
     U2, hist2, _ = M.mpc_solve(C, x2, warm, 0.02, "euler", lr=0.03, iters=50, return_mode="best")
     assert np.abs(U2 - z["ctrl_seq"][:, 1]).max() < 0.05 * 0.03
     assert rel_err(hist2.T, z["ctrl_costs"][:, 1]) < 1e-4
+
+
+def test_oracle_cfg4_shape_vs_reference():
+    """the benchmarked job's shape (cfg4 weights, bench.py's first 64 instances, H=50, RK4, 20 Adam iterations) recorded
+    from the reference itself (make_golden.gen_cfg4_shape): cost history, dJ/dU at iteration 0, controls, best cost"""
+    from oracle.phnn_oracle import OracleModel, set_threads
+    import os
+    z, _ = load_golden("cfg4_shape")
+    _, sd = load_golden("cartpole_h256")
+    set_threads(os.cpu_count() or 1)
+    M = OracleModel(sd, "phnn")
+    C = M.cost_struct(z["Q"], z["R"], z["xt"], float(z["bounds"][0]), float(z["bounds"][1]))
+    B, H, iters = z["x0"].shape[0], int(z["H"]), int(z["iters"])
+    U0 = np.zeros((B, H, 1), np.float32)
+    U, hist, best = M.mpc_solve(C, z["x0"], U0, float(z["dt"]), "rk4", lr=float(z["lr"]), iters=iters)
+    assert rel_err(hist, z["rk4_hist"]) < 1e-4 and rel_err(best, z["rk4_best"]) < 1e-4
+    assert np.abs(U - z["rk4_U_last"]).max() < 0.02 * float(z["lr"]) + 1e-5
+    _, g0 = M.cost_grad(C, z["x0"], U0, float(z["dt"]), "rk4")
+    assert rel_err(g0, z["rk4_grad0"]) < 1e-4
