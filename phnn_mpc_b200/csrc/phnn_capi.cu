@@ -4,7 +4,10 @@
 #include "../../include/phnn_mpc.h"
 #include "phnn_kernel.cuh"
 #include "phnn_tc_kernel.cuh"
+#include "phnn_tc16_kernel.cuh"
 #include "phnn_lat_kernel.cuh"
+
+#include <cuda_fp16.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -27,6 +30,8 @@ struct phnn_pack {
     unsigned char* d_wtc;
     float* d_small_tc;
     unsigned char* d_wtc2;  // tensor_mode 2 weights (TF32 hi tiles + BF16 correction tiles)
+    unsigned char* d_wtc16; // tensor_mode 4 weights (FP16 hi | lo tiles, scaled) and its small-layer records
+    float* d_small16;
     size_t small_floats;
     KParams base;  // model constants filled in once
 };
@@ -193,6 +198,96 @@ static void fill_tc_small(const phnn_model_desc* d, std::vector<float>& s) {
     }
 }
 
+// ---- tensor_mode 4 (phnn_tc16_kernel.cuh) ------------------------------------------------------------------
+static float pow2f(int e) { return std::ldexp(1.0f, e); }
+static int floor_log2(float x) {  // floor(log2 x) for finite x > 0
+    int e;
+    std::frexp(x, &e);
+    return e - 1;
+}
+struct Tc16Scales {
+    int eB, eA, eD, eE, wexp;  // S_B = 2^eB (weights), S_a = 2^eA (a1), S_delta = 2^eD (w3 in delta2), S_e = 2^eE (w3 in e2)
+};
+// Exact power-of-two scales that put every FP16 operand of the four products in [~2^-2, 2^15] (FP16: 11-bit
+// significand, normal range 6.1e-5 .. 65504; hi + lo keeps 22 bits as long as |lo| >= 6.1e-5, i.e. |x| >= 0.25):
+//   weights    max |W2| S_B in [2^9, 2^10)                       a1 in [-1, 1]: S_a = 2^9
+//   delta2 = (1 - a2^2) w3: max |w3| S_delta in [2^9, 2^10)
+//   da1 = s1 (W1 w'): |da1| <= rho1 max|w'|, rho1 = max row L1 norm of W1; max|w'| < 2^(wexp+1) <= 2^14 / rho1
+//   e2 = -2 a2 s2 dz2 w3 S_e: |2 a2 s2| <= 0.77, |dz2| <= rho2 max|da1| (rho2 = max row L1 norm of W2): bound <= 2^15
+static Tc16Scales tc16_scales(const phnn_model_desc* d) {
+    const int h = d->h, n = d->n;
+    float maxW2 = 0.f, maxw3 = 0.f, rho1 = 0.f, rho2 = 0.f;
+    for (int j = 0; j < h; ++j) {
+        float r1 = 0.f, r2 = 0.f;
+        for (int i = 0; i < n; ++i) r1 += std::fabs(d->W1[j * n + i]);
+        for (int k = 0; k < h; ++k) {
+            const float a = std::fabs(d->W2[(size_t)j * h + k]);
+            r2 += a;
+            maxW2 = std::fmax(maxW2, a);
+        }
+        rho1 = std::fmax(rho1, r1);
+        rho2 = std::fmax(rho2, r2);
+        maxw3 = std::fmax(maxw3, std::fabs(d->W3[j]));
+    }
+    maxW2 = std::fmax(maxW2, 1e-30f); maxw3 = std::fmax(maxw3, 1e-30f);
+    rho1 = std::fmax(rho1, 1e-30f); rho2 = std::fmax(rho2, 1e-30f);
+    Tc16Scales s;
+    s.eB = 9 - floor_log2(maxW2);
+    s.eA = 9;
+    s.eD = 9 - floor_log2(maxw3);
+    s.wexp = 13 - (floor_log2(rho1) + 1);                 // rho1 2^(wexp+1) <= 2^14
+    const float bound = 0.77f * maxw3 * rho2 * rho1 * pow2f(s.wexp + 1);
+    s.eE = 15 - (floor_log2(bound) + 1);                  // bound 2^eE <= 2^15
+    return s;
+}
+
+// [P: W2 | W2^T][kb][h rows x 128 B], row n = [b_hi (32 fp16) | b_lo (32 fp16)] of B[n][32 kb ..] * S_B, K-major SWIZZLE_128B
+static void fill_tc16_big(const phnn_model_desc* d, const Tc16Scales& sc, std::vector<unsigned char>& out) {
+    const int h = d->h, nkb = h / 32;
+    const size_t tile = (size_t)h * 128;
+    const float SB = pow2f(sc.eB);
+    out.assign((size_t)2 * nkb * tile, 0);
+    for (int P = 0; P < 2; ++P)
+        for (int kb = 0; kb < nkb; ++kb)
+            for (int n = 0; n < h; ++n)
+                for (int c = 0; c < 32; ++c) {
+                    const int K = kb * 32 + c;
+                    const float val = SB * ((P == 0) ? d->W2[(size_t)n * h + K] : d->W2[(size_t)K * h + n]);
+                    const __half hi = __float2half_rn(val);
+                    const __half lo = __float2half_rn(val - __half2float(hi));
+                    const size_t row = ((size_t)(P * nkb + kb)) * tile + (size_t)(n >> 3) * 1024 + (n & 7) * 128;
+                    const int j0 = c, j1 = 32 + c;  // 16-bit column j sits at byte 2 j of the row (16-byte chunk j / 8, swizzled)
+                    memcpy(&out[row + ((((j0 >> 3) ^ (n & 7)) & 7) << 4) + (j0 & 7) * 2], &hi, 2);
+                    memcpy(&out[row + ((((j1 >> 3) ^ (n & 7)) & 7) << 4) + (j1 & 7) * 2], &lo, 2);
+                }
+}
+
+// field-major records (layout in Tc16Shape): field f, pair P -> float4 at (f * h/2 + P)
+static void fill_tc16_small(const phnn_model_desc* d, const Tc16Scales& sc, std::vector<float>& s) {
+    const int h = d->h, n = d->n, np = h / 2;
+    const bool has_r = d->kind == PHNN_KIND_PHNN;
+    s.assign((size_t)(has_r ? 12 : 5) * np * 4, 0.f);
+    auto at = [&](int f, int P, int half, int o) -> float& { return s[((size_t)f * np + P) * 4 + half * 2 + o]; };
+    const float SD = pow2f(sc.eD), SE = pow2f(sc.eE);
+    for (int k = 0; k < h; ++k) {
+        const int P = k >> 1, o = k & 1;
+        at(0, P, 0, o) = d->W1[k * n + 0]; at(0, P, 1, o) = d->W1[k * n + 1];
+        at(1, P, 0, o) = d->W1[k * n + 2]; at(1, P, 1, o) = d->W1[k * n + 3];
+        at(2, P, 0, o) = d->b1[k];
+        at(3, P, 0, o) = d->b2[k];         at(3, P, 1, o) = d->W3[k] * SD;
+        at(4, P, 0, o) = -2.f * d->W3[k] * SE;
+        if (!has_r) continue;
+        at(2, P, 1, o) = d->br1[k];
+        at(5, P, 0, o) = d->Wr1[k * n + 0]; at(5, P, 1, o) = d->Wr1[k * n + 1];
+        at(6, P, 0, o) = d->Wr1[k * n + 2]; at(6, P, 1, o) = d->Wr1[k * n + 3];
+        for (int a = 0; a < n; ++a)
+            for (int b = a; b < n; ++b) {
+                const int i = sym_idx(a, b);
+                at(7 + i / 2, P, i & 1, o) = 0.5f * (d->Wr2[(size_t)(a * n + b) * h + k] + d->Wr2[(size_t)(b * n + a) * h + k]);
+            }
+    }
+}
+
 template <class SH>
 static void fill_small(const phnn_model_desc* d, std::vector<float>& s) {
     constexpr int NS = SH::NS, HID = SH::HID, NN = SH::NN;
@@ -238,6 +333,12 @@ static cudaError_t set_smem_limits(int mk, int n, int h) {
     if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
         e = cudaFuncSetAttribute(phnn_tc_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                  (int)TcShape<MK, NS, HID>::SMEM_BYTES);
+    PHNN_TC_SHAPES(X)
+#undef X
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                 (int)Tc16Shape<MK, NS, HID>::SMEM_BYTES);
     PHNN_TC_SHAPES(X)
 #undef X
 #define X(MK, NS, HID)                                                                                                  \
@@ -308,6 +409,22 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         if (e == cudaSuccess) e = cudaMalloc(&pk->d_small_tc, stc.size() * sizeof(float));
         if (e == cudaSuccess) e = cudaMemcpy(pk->d_wtc, wtc.data(), wtc.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(pk->d_small_tc, stc.data(), stc.size() * sizeof(float), cudaMemcpyHostToDevice);
+        std::vector<unsigned char> w16;
+        std::vector<float> s16;
+        const Tc16Scales sc = tc16_scales(d);
+        fill_tc16_big(d, sc, w16);
+        fill_tc16_small(d, sc, s16);
+        if (e == cudaSuccess) e = cudaMalloc(&pk->d_wtc16, w16.size());
+        if (e == cudaSuccess) e = cudaMemcpy(pk->d_wtc16, w16.data(), w16.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&pk->d_small16, s16.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(pk->d_small16, s16.data(), s16.size() * sizeof(float), cudaMemcpyHostToDevice);
+        pk->base.s16[0] = pow2f(-(sc.eA + sc.eB));
+        pk->base.s16[1] = pow2f(-(sc.eD + sc.eB));
+        pk->base.s16[2] = pow2f(-sc.eB);
+        pk->base.s16[3] = pow2f(-(sc.eE + sc.eB));
+        pk->base.s16[4] = pow2f(sc.eA);
+        pk->base.s16[5] = pow2f(-sc.eD);
+        pk->base.wexp16 = sc.wexp;
         pk->tc_mode = 2;  // TF32 + BF16 correction product: FP32-level accuracy at 2/3 of the MMA work of 3xTF32
         pk->tc_min_batch = 1;  // measured: the tcgen05 kernel beats the FP32-FMA kernel at every batch size (tools/gpu_crossover.py)
     }
@@ -318,6 +435,8 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         cudaFree(pk->d_wtc);
         cudaFree(pk->d_wtc2);
         cudaFree(pk->d_small_tc);
+        cudaFree(pk->d_wtc16);
+        cudaFree(pk->d_small16);
         delete pk;
         return cuda_fail(e, "phnn_pack_create");
     }
@@ -331,6 +450,8 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
     P.wbig = pk->d_big;
     P.wtc = pk->d_wtc;
     P.wsmall_tc = pk->d_small_tc;
+    P.wtc16 = pk->d_wtc16;
+    P.wsmall16 = pk->d_small16;
     for (int a = 0; a < n; ++a)
         for (int b = 0; b < n; ++b)
             P.Jm[a * n + b] = (mk == MK_CANON) ? d->J[a * n + b] : (d->J[a * n + b] - d->J[b * n + a]);
@@ -359,6 +480,8 @@ extern "C" int phnn_pack_destroy(phnn_pack* pk) {
     cudaFree(pk->d_wtc);
     cudaFree(pk->d_wtc2);
     cudaFree(pk->d_small_tc);
+    cudaFree(pk->d_wtc16);
+    cudaFree(pk->d_small16);
     delete pk;
     return 0;
 }
@@ -366,7 +489,7 @@ extern "C" int phnn_pack_destroy(phnn_pack* pk) {
 extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) {
     if (!pk || !key) return fail(PHNN_E_ARG, "phnn_pack_set_option: null argument");
     if (!strcmp(key, "tensor_mode")) {
-        if (value != 0 && value != 1 && value != 2 && value != 3) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1, 2 or 3");
+        if (value < 0 || value > 4) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1, 2, 3 or 4");
         if (value != 0 && !pk->d_wtc) return fail(PHNN_E_UNSUPPORTED, "no tcgen05 kernel for this model shape");
         pk->tc_mode = (int)value;
         return 0;
@@ -460,7 +583,8 @@ template <class SH>
 static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
     static_assert((3 * SH::HID * 128 * 4) % 65536 == 0, "tape prefetch granularity");
     const long long tiles = (P.B + SH::TM - 1) / SH::TM;
-    auto kern = phnn_tc_kernel<SH::MK, SH::NS, SH::HID>;
+    using SH16 = Tc16Shape<SH::MK, SH::NS, SH::HID>;
+    const bool gen2 = pk->tc_mode == 4;  // FP16 hi/lo operands, A in tensor memory (phnn_tc16_kernel.cuh)
     P.tc_split = pk->tc_mode;  // 1 plain TF32, 2 TF32 + BF16 correction product, 3 3xTF32
     if (pk->tc_mode == 2) P.wtc = pk->d_wtc2;
     P.ng = 1;
@@ -491,7 +615,10 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
             CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
         }
     }
-    kern<<<(unsigned)grid, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
+    if (gen2)
+        phnn_tc16_kernel<SH::MK, SH::NS, SH::HID><<<(unsigned)grid, SH16::THREADS, SH16::SMEM_BYTES, stream>>>(P);
+    else
+        phnn_tc_kernel<SH::MK, SH::NS, SH::HID><<<(unsigned)grid, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

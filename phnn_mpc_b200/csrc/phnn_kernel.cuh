@@ -83,6 +83,12 @@ struct KParams {
     const unsigned char* wtc;  // tcgen05 path: pre-swizzled hi/lo K-blocks of W2 and W2^T
     const float* wsmall_tc;    // tcgen05 path: per-hidden-unit records of the small layers
     int tc_split;              // 3 = 3xTF32 (FP32-level accuracy), 1 = plain TF32
+    // second-generation tcgen05 kernel (phnn_tc16_kernel.cuh, tensor_mode 4): FP16 hi/lo operands, A in tensor memory
+    const unsigned char* wtc16;  // pre-swizzled K-blocks of W2 and W2^T, rows of [b_hi (32 fp16) | b_lo (32 fp16)], scaled by S_B
+    const float* wsmall16;       // field-major small-layer records (Tc16Shape)
+    float s16[8];                // exact power-of-two scales: [0] 1/(S_a S_B), [1] 1/(S_delta S_B), [2] 1/S_B, [3] 1/(S_e S_B),
+                                 // [4] S_a, [5] 1/S_delta
+    int wexp16;                  // per-instance adjoint scale: max |w'| lands in [2^wexp16, 2^(wexp16+1))
     // model constants
     float Jm[16];  // MK 0/1: J - J^T ; MK 2: the canonical J buffer
     float Gv[4];

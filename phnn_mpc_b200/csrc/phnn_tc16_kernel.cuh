@@ -1,0 +1,846 @@
+// phnn_tc16_kernel.cuh -- second-generation tcgen05 kernel of the fused pHNN-MPC path (sm_100a), tensor_mode 4.
+//
+// Same jobs, same per-instance arithmetic (run_job) and same four h x h tensor products per (forward, adjoint) pair
+// of evaluations as phnn_tc_kernel.cuh; what changes is how the operands reach the tensor cores, because the first
+// kernel was bound by the shared-memory data pipe (ncu, profiles/r01_*: LDS 35 %, tensor-core operand reads 28 %,
+// STS 15 %, tape 15 % of its wavefronts) and by the L2 -> SM weight stream, not by the tensor pipe:
+//
+//   * FP32-level accuracy from THREE FP16 products instead of TF32 + a double-depth BF16 correction.
+//     x = hi + lo with hi = fp16(x), lo = fp16(x - hi) carries 22 mantissa bits; A B ~= Ahi Bhi + Ahi Blo + Alo Bhi,
+//     accumulated in FP32 in TMEM (every dropped term is <= 2^-24 of |a||b|).  FP16 has a 5-bit exponent, so every
+//     operand is scaled by an exact power of two into [~2^-2, 2^15]: static scales for the weights, a1 and delta2
+//     (chosen on the host from the weight norms), one scale PER INSTANCE AND EVALUATION for the adjoint operands
+//     (everything downstream of the cotangent w is linear in it; the result is scaled back exactly).  6 MMAs of
+//     K = 16 per 32-unit K-block instead of 8: 3/4 of the tensor time, and the weight tile of a K-block is
+//     [b_hi | b_lo] = 32 KB at h = 256 instead of 64 KB: half the L2 -> SM stream and half the bulk-copy writes.
+//   * OPERAND A NEVER TOUCHES SHARED MEMORY.  [a_hi (32 fp16) | a_lo (32 fp16)] of a K-block is 32 TMEM columns --
+//     exactly the 32 accumulator columns the element threads have just consumed to produce it.  The products whose
+//     operand is the epilogue of the previous product (delta2 from z2, e2 from dz2) are written IN PLACE over the
+//     consumed accumulator block with tcgen05.st; the products fed from the instance state (a1, da1) are written into
+//     the other, idle accumulator (all 8 K-blocks fit: no ring, no empty-slot wait).  tcgen05.mma reads A from TMEM
+//     (the .ts form): no STS, no fence.proxy.async, no tensor-core A reads on the shared-memory pipe.
+//   * mma-style FRAGMENTS instead of thread = instance.  tcgen05.ld.16x256b hands a thread two instances (TMEM lanes
+//     g, g + 8) x four pairs of adjacent hidden units of every K-block, so every small-layer record (W1, b1, Wr1, Wr2,
+//     w3 ... of a pair of units) loaded from shared memory serves two instances, the four lanes of a quad read four
+//     consecutive records (64 contiguous bytes) instead of one warp-uniform address, and the reductions over the
+//     hidden dimension finish with two shuffles inside the quad: no shared-memory exchange, no named barriers.
+//     Each instance is owned by two lanes of its quad for the per-instance algebra (run_job), as before.
+//
+// Roles: warps 0..7 element threads, warp 8 MMA issuer (one lane), warp 9 weight producer (cp.async.bulk ring).
+#pragma once
+#include "phnn_tc_kernel.cuh"
+
+namespace phnn {
+
+template <int MK_, int NS_, int HID_>
+struct Tc16Shape {
+    static_assert((MK_ == MK_PHNN || MK_ == MK_CANON) && NS_ == 4, "tensor-core path: cart-pole pHNN (fixed G) and canonical pHNN, n = 4");
+    static constexpr int MK = MK_, NS = NS_, HID = HID_, NN = NS * NS;
+    static constexpr bool HAS_R = (MK != MK_CANON);
+    static constexpr int TM = 128;            // instances per tile (UMMA M)
+    static constexpr int NEW = 8;             // element warps: (TMEM lane quadrant, 16-lane half)
+    static constexpr int NKB = HID / 32;      // K-blocks of 32 hidden units
+    static constexpr int NP = HID / 2;        // pairs of adjacent hidden units
+    static constexpr int B_TILE = HID * 128;  // bytes of the weight tile of one K-block: rows of [b_hi (32 fp16) | b_lo (32 fp16)]
+    static constexpr int NBE = (HID >= 256) ? 5 : 8;  // weight ring entries
+    static constexpr int TMEM_COLS = (2 * HID <= 32) ? 32 : (2 * HID <= 64) ? 64 : (2 * HID <= 128) ? 128 : (2 * HID <= 256) ? 256 : 512;
+    // small weights: field-major arrays of float4, one entry per pair P of adjacent hidden units (2P, 2P+1); every
+    // half of a field is the pair {unit 2P, unit 2P+1}
+    //   F0 {W1[.][0]} {W1[.][1]}   F1 {W1[.][2]} {W1[.][3]}   F2 {b1} {br1}   F3 {b2} {w3 * S_delta}   F4 {-2 w3 * S_e} {0}
+    //   F5 {Wr1[.][0]} {Wr1[.][1]} F6 {Wr1[.][2]} {Wr1[.][3]}
+    //   F7..F11 the 10 symmetrised R_net output weights (Wr2[ab][.] + Wr2[ba][.])/2, a <= b, two per field
+    static constexpr int NF = HAS_R ? 12 : 5;
+    static constexpr int SMALL = NF * NP * 4;  // floats
+    // shared memory map (bytes): barriers in [0, 256), TMEM address at 512, scheduler slot at 768
+    static constexpr int OFF_B = 1024;
+    static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE;
+    static constexpr int SMEM_BYTES = OFF_SMALL + SMALL * 4;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static constexpr int B_AFULL = 0, B_BFULL = NKB, B_BEMPTY = NKB + NBE, B_ACC = NKB + 2 * NBE, B_SMALL = B_ACC + 2;
+    static_assert((B_SMALL + 1) * 8 <= 256, "barriers live in the first 256 bytes");
+    // 8 element warps (two warpgroups) + one warpgroup holding the MMA issuer, the weight producer and two idle warps:
+    // setmaxnreg moves registers from the latter to the element warps (the per-thread state of two instances plus the
+    // fragment buffers do not fit the 168 registers a 384-thread CTA gets at launch)
+    static constexpr int THREADS = 32 * NEW + 128;
+    static constexpr int REGS_ELEM = 224, REGS_AUX = 48;
+    static_assert(32 * NEW * REGS_ELEM + 128 * REGS_AUX <= 65536, "register file");
+};
+
+// ---- tcgen05 helpers of this kernel ---------------------------------------------------------------------
+// D[tmem] (+)= A[tmem] * B[smem descriptor], FP16 operands, FP32 accumulation (K = 16 per instruction)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// 16 TMEM lanes x 32 columns as the mma-style fragment: r[4 k + 2 rsel + e] = (lane base + lane/4 + 8 rsel, column 8 k + 2 (lane%4) + e)
+__device__ __forceinline__ void tmem_ld_frag_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// 16 TMEM lanes x 32 columns of packed pairs: q[2 k + rsel] = (lane base + lane/4 + 8 rsel, column 4 k + lane%4), k = 0..7
+__device__ __forceinline__ void tmem_st_pairs(uint32_t taddr, const uint32_t (&q)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]), "r"(q[8]), "r"(q[9]), "r"(q[10]),
+        "r"(q[11]), "r"(q[12]), "r"(q[13]), "r"(q[14]), "r"(q[15])
+        : "memory");
+}
+// visit the NKB 32-column blocks of an accumulator as fragments, the next block's load in flight
+template <int NKB, class F>
+__device__ __forceinline__ void for_acc_frags(uint32_t tacc, F&& body) {
+    uint32_t ra[16], rb[16];
+    tmem_ld_frag_issue(tacc, ra);
+#pragma unroll 1
+    for (int b = 0; b < NKB; b += 2) {
+        tmem_wait(ra);
+        tmem_ld_frag_issue(tacc + (b + 1) * 32, rb);
+        body(b, ra);
+        tmem_wait(rb);
+        if (b + 2 < NKB) tmem_ld_frag_issue(tacc + (b + 2) * 32, ra);
+        body(b + 1, rb);
+    }
+}
+// (already scaled) pair -> fp16x2 hi and fp16x2 lo = fp16(t - hi); element .x sits in the low half (even K index)
+__device__ __forceinline__ void split_f16x2(float2 t, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(t.y), "f"(t.x));
+    float hx, hy;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(hx), "=f"(hy) : "r"(hi));
+    const float2 l = sub2(t, make_float2(hx, hy));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l.y), "f"(l.x));
+}
+__device__ __forceinline__ float2 frag2(const uint32_t (&r)[16], int k, int rsel) {
+    return make_float2(__uint_as_float(r[4 * k + 2 * rsel]), __uint_as_float(r[4 * k + 2 * rsel + 1]));
+}
+
+template <class SH> struct Tc16Ctx;
+template <class SH>
+__device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
+template <class SH>
+__device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u, const float (&v)[4],
+                                              float (&xbar)[4], float& ubar);
+
+template <class SH>
+struct Tc16Ctx {
+    static constexpr int NS = SH::NS;
+    static constexpr int TW = SH::TM;
+    __device__ static int ws_extra(const KParams& p) { return tc_ws_extra(SH::HID, p.T, p.S); }
+    __device__ __forceinline__ void set_eval(int e) { ev = e; }
+    int row;         // the instance this lane owns for the per-instance algebra (= its TMEM lane)
+    int lane, cq;    // lane; position in the quad (lanes of a quad share two instances: A = TMEM lane base + lane/4, B = A + 8)
+    int srcA, srcB;  // lanes whose own instance is A / B of this quad
+    int tid;         // element thread index (tape layout)
+    uint32_t tl16;   // TMEM base address with the lane offset of this warp's 16-lane block
+    uint32_t qdone;  // products whose accumulator this thread has waited for
+    uint32_t qfeed;  // products this thread has fed (operand A written for)
+    float* sck;      // per tile: R_net sums [0,10) and grad H [10,14) of every forward evaluation, [T*S][16][128]
+    int ev;          // index of the evaluation in flight (t * S + s)
+    float* tape;     // per CTA: a2, a1, g1 of every forward evaluation of the unit in flight: [T*S][3][NKB][4][256] float4
+    bool store;
+
+    __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(phnn_smem); }
+    __device__ __forceinline__ const float4* fields() const { return reinterpret_cast<const float4*>(phnn_smem + SH::OFF_SMALL); }
+    __device__ __forceinline__ void gbar() const { __syncwarp(); }  // the co-owners of an instance are lanes of one quad
+    __device__ __forceinline__ float own(float a, float b) const { return (cq & 2) ? b : a; }
+    __device__ __forceinline__ float fromA(float v) const { return __shfl_sync(0xffffffffu, v, srcA); }
+    __device__ __forceinline__ float fromB(float v) const { return __shfl_sync(0xffffffffu, v, srcB); }
+    // partial sums over this lane's hidden units for instances A and B -> the total of the lane's own instance
+    // (both co-owners add the same two partial sums: bit-identical copies)
+    __device__ __forceinline__ float quad_own_sum(float sA, float sB) const {
+        const bool ob = (cq & 2) != 0;
+        float r = (ob ? sB : sA) + __shfl_xor_sync(0xffffffffu, ob ? sA : sB, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        return r;
+    }
+    // wait for the next product's accumulator; returns its column base
+    __device__ __forceinline__ uint32_t acc_wait() {
+        const uint32_t q = qdone++;
+        mbar_wait(&bars()[SH::B_ACC + (q & 1u)], (q >> 1) & 1u);
+        tc_fence_after();
+        return (q & 1u) * SH::HID;
+    }
+    // column base of operand A of the product being fed: always the accumulator the product does NOT write -- the
+    // idle one for the first product of an evaluation, the one being consumed (in place) for the second
+    __device__ __forceinline__ uint32_t feed_col() const { return ((qfeed & 1u) ^ 1u) * SH::HID; }
+    // operand A of K-block kb: v[rsel][k] = the pair of units (32 kb + 8 k + 2 cq, +1) of instance rsel, times `scale`
+    __device__ __forceinline__ void put_block(int kb, const float2 (&v)[2][4], float scale) {
+        uint32_t q[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int rsel = 0; rsel < 2; ++rsel) split_f16x2(mul2(v[rsel][k], bc2(scale)), q[2 * k + rsel], q[2 * (4 + k) + rsel]);
+        tmem_st_pairs(tl16 + feed_col() + kb * 32, q);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars()[SH::B_AFULL + kb]);
+    }
+    __device__ __forceinline__ void end_feed() { ++qfeed; }
+    // float4 slot of the tape: array which (0 a2, 1 a1, 2 g1), K-block kb, slot = 2 rsel + (k >> 1)
+    __device__ __forceinline__ float4* tape4(int which, int kb, int slot) const {
+        return reinterpret_cast<float4*>(tape) + (((size_t)ev * 3 + which) * (SH::NKB * 4) + kb * 4 + slot) * 256 + tid;
+    }
+    template <bool LAST>
+    __device__ __forceinline__ void tape_load(int which, int kb, float4 (&v)[4]) const {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v[s] = LAST ? __ldcs(tape4(which, kb, s)) : __ldcg(tape4(which, kb, s));
+    }
+    __device__ __forceinline__ void begin_unit(const KParams& p, long long tile) {
+        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, TW, ws_extra(p));
+        sck = p.ws ? p.ws + (size_t)tile * tile_floats + ws_floats_per_tile(NS, p.T, p.S, TW, 0) : nullptr;
+    }
+    __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[4], float u, float (&f)[4], float& H) {
+        tc16_eval_fwd(*this, p, y, u, f, H);
+    }
+    __device__ __forceinline__ void eval_vjp(const KParams& p, const float (&y)[4], float u, const float (&v)[4],
+                                             float (&xbar)[4], float& ubar) {
+        tc16_eval_vjp(*this, p, y, u, v, xbar, ubar);
+    }
+};
+
+// pair (k of this lane's four) of K-block kb: units 32 kb + 8 k + 2 cq, +1
+template <class SH>
+__device__ __forceinline__ int tc16_pair(const Tc16Ctx<SH>& c, int kb, int k) { return kb * 16 + k * 4 + c.cq; }
+// the pair of units k of a tape float4 slot pair (slots 2 rsel, 2 rsel + 1 hold k = 0,1 and k = 2,3)
+__device__ __forceinline__ float2 tape_pair(const float4 (&t)[4], int rsel, int k) {
+    const float4& q = t[2 * rsel + (k >> 1)];
+    return (k & 1) ? zw(q) : xy(q);
+}
+__device__ __forceinline__ float4 pack4(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+
+// R_net hidden layer and symmetrised output sums for pairs [K0, K1) of this lane's four in K-block kb, both instances
+template <int K0, int K1, class SH>
+__device__ __forceinline__ void tc16_rfwd(const Tc16Ctx<SH>& c, int kb, const float (&yA)[4], const float (&yB)[4], float2 (&SpA)[10],
+                                          float2 (&SpB)[10]) {
+    const float4* F = c.fields();
+#pragma unroll
+    for (int k = K0; k < K1; ++k) {
+        const int P = tc16_pair(c, kb, k);
+        const float4 u01 = F[5 * SH::NP + P], u23 = F[6 * SH::NP + P];
+        const float2 br1 = zw(F[2 * SH::NP + P]);
+        const float2 rA = tanh_tc2(pair_affine(u01, u23, yA, br1));
+        const float2 rB = tanh_tc2(pair_affine(u01, u23, yB, br1));
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 cc = F[(7 + j) * SH::NP + P];
+            SpA[2 * j] = fma2(xy(cc), rA, SpA[2 * j]);
+            SpA[2 * j + 1] = fma2(zw(cc), rA, SpA[2 * j + 1]);
+            SpB[2 * j] = fma2(xy(cc), rB, SpB[2 * j]);
+            SpB[2 * j + 1] = fma2(zw(cc), rB, SpB[2 * j + 1]);
+        }
+        sched_fence();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// f(y,u), H(y) for the tile's 128 instances (src/pHNN.py:52-100, src/pHNN_canonical.py:172-273)
+// ---------------------------------------------------------------------------------------
+template <class SH>
+__device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4],
+                                              float& Hval) {
+    constexpr int NKB = SH::NKB, NP = SH::NP;
+    const float4* F = c.fields();
+    float z[4];
+    Canon cq = {};
+    if constexpr (SH::MK == MK_CANON) {
+        cq = canon_of(p, y[1]);
+        z[0] = y[0]; z[1] = y[1];
+        z[2] = p.ma * y[2] + cq.beta * y[3];  // p = M(q) qdot
+        z[3] = cq.beta * y[2] + p.mc * y[3];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z[i] = y[i];
+    }
+    // the two instances of this quad (for kind pHNN z = y; the canonical model has no R_net, which is what reads y)
+    float zA[4], zB[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { zA[i] = c.fromA(z[i]); zB[i] = c.fromB(z[i]); }
+    float2 SpA[10], SpB[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { SpA[i] = make_float2(0.f, 0.f); SpB[i] = make_float2(0.f, 0.f); }
+    // ---- phase A: a1 = tanh(W1 z + b1) -> operand A of product 1 (z2 = W2 a1), into the idle accumulator ----
+    {
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) {
+            float2 a[2][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int P = tc16_pair(c, kb, k);
+                const float4 w01 = F[P], w23 = F[NP + P];
+                const float2 b1 = xy(F[2 * NP + P]);
+                a[0][k] = tanh_tc2(pair_affine(w01, w23, zA, b1));
+                a[1][k] = tanh_tc2(pair_affine(w01, w23, zB, b1));
+                if (k & 1) sched_fence();
+            }
+            if (c.tape) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) *c.tape4(1, kb, s) = pack4(a[s >> 1][2 * (s & 1)], a[s >> 1][2 * (s & 1) + 1]);  // read back in phase C
+            }
+            c.put_block(kb, a, p.s16[4]);
+            if constexpr (SH::HAS_R) {
+                if (kb >= PHNN_TC_RSKEW) tc16_rfwd<0, 2>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
+            }
+        }
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rfwd<0, 2>(c, kb, zA, zB, SpA, SpB);
+        }
+        c.end_feed();
+    }
+    // ---- phase B: a2, H, delta2 -> operand A of product 2 (g1 = W2^T delta2), in place over the consumed z2 block ----
+    float Hown;
+    {
+        const uint32_t tacc = c.acc_wait();
+        const float isz = p.s16[0];
+        float2 HpA = make_float2(0.f, 0.f), HpB = make_float2(0.f, 0.f);
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&zr)[16]) {
+            float2 d[2][4], a2[2][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 m = F[3 * NP + tc16_pair(c, kb, k)];  // {b2 pair, w3 * S_delta pair}
+#pragma unroll
+                for (int rsel = 0; rsel < 2; ++rsel) {
+                    const float2 t = tanh_tc2(fma2(frag2(zr, k, rsel), bc2(isz), xy(m)));
+                    if (rsel) HpB = fma2(zw(m), t, HpB); else HpA = fma2(zw(m), t, HpA);
+                    d[rsel][k] = mul2(one_minus_sq(t), zw(m));
+                    a2[rsel][k] = t;
+                }
+                if (k & 1) sched_fence();
+            }
+            if (c.tape) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) __stcs(c.tape4(0, kb, s), pack4(a2[s >> 1][2 * (s & 1)], a2[s >> 1][2 * (s & 1) + 1]));
+            }
+            c.put_block(kb, d, 1.0f);
+            if constexpr (SH::HAS_R) {
+                if (kb >= PHNN_TC_RSKEW) tc16_rfwd<2, 4>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
+            }
+        });
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rfwd<2, 4>(c, kb, zA, zB, SpA, SpB);
+        }
+        c.end_feed();
+        Hown = c.quad_own_sum(HpA.x + HpA.y, HpB.x + HpB.y) * p.s16[5];
+    }
+    // ---- phase C: dH = W1^T (s1 * g1) ----
+    float dH[4];
+    {
+        float2 GA[4], GB[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { GA[i] = make_float2(0.f, 0.f); GB[i] = make_float2(0.f, 0.f); }
+        const float isg = p.s16[1];
+        if (c.tape) {
+            // a1 comes back from the tape (written by this thread in phase A, still in L2)
+            float4 an[4];
+            c.template tape_load<false>(1, 0, an);
+            const uint32_t tacc = c.acc_wait();
+            for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16]) {
+                float4 ac[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) ac[s] = an[s];
+                if (kb + 1 < NKB) c.template tape_load<false>(1, kb + 1, an);
+                float2 g[2][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int P = tc16_pair(c, kb, k);
+                    const float4 w01 = F[P], w23 = F[NP + P];
+#pragma unroll
+                    for (int rsel = 0; rsel < 2; ++rsel) {
+                        g[rsel][k] = mul2(frag2(gr, k, rsel), bc2(isg));
+                        const float2 t = mul2(one_minus_sq(tape_pair(ac, rsel, k)), g[rsel][k]);
+                        if (rsel) pair_scatter(w01, w23, t, GB); else pair_scatter(w01, w23, t, GA);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) __stcs(c.tape4(2, kb, s), pack4(g[s >> 1][2 * (s & 1)], g[s >> 1][2 * (s & 1) + 1]));
+            });
+        } else {
+            const uint32_t tacc = c.acc_wait();
+            for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16]) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int P = tc16_pair(c, kb, k);
+                    const float4 w01 = F[P], w23 = F[NP + P];
+                    const float2 b1 = xy(F[2 * NP + P]);
+                    const float2 aA = tanh_tc2(pair_affine(w01, w23, zA, b1));
+                    const float2 aB = tanh_tc2(pair_affine(w01, w23, zB, b1));
+                    pair_scatter(w01, w23, mul2(one_minus_sq(aA), mul2(frag2(gr, k, 0), bc2(isg))), GA);
+                    pair_scatter(w01, w23, mul2(one_minus_sq(aB), mul2(frag2(gr, k, 1), bc2(isg))), GB);
+                    if (k & 1) sched_fence();
+                }
+            });
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dH[i] = c.quad_own_sum(GA[i].x + GA[i].y, GB[i].x + GB[i].y);
+        tc_fence_before();
+    }
+    float Sp[12];
+    if constexpr (SH::HAS_R) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) Sp[i] = c.quad_own_sum(SpA[i].x + SpA[i].y, SpB[i].x + SpB[i].y);
+    }
+    if (c.tape && c.store) {
+        // the adjoint evaluation at this stage state reuses the R_net sums and grad H
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) c.sck[((size_t)c.ev * 16 + i) * 128 + c.row] = Sp[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.sck[((size_t)c.ev * 16 + 10 + i) * 128 + c.row] = dH[i];
+    }
+    Hval = Hown + p.b3;
+    if constexpr (SH::MK == MK_CANON) {
+        float pd[2];
+        tc_canon_pdot(p, dH, u, pd);
+        f[0] = cq.n11 * z[2] + cq.n12 * z[3];  // qdot = M^-1 p
+        f[1] = cq.n12 * z[2] + cq.n22 * z[3];
+        f[2] = cq.n11 * pd[0] + cq.n12 * pd[1];  // qddot ~= M^-1 pdot
+        f[3] = cq.n12 * pd[0] + cq.n22 * pd[1];
+    } else {
+        float S[4][4];
+        tc_make_S(p, Sp, S);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float s = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float Rab = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) Rab = fmaf(S[a][k], S[b][k], Rab);
+                s = fmaf(p.Jm[a * 4 + b] - Rab, dH[b], s);
+            }
+            f[a] = s + p.Gv[a] * u;
+        }
+    }
+}
+
+// R_net backward chain for pairs [K0, K1) of K-block kb, both instances: X += Wr1[.]^T (1 - r^2) (Wr2sym[.] . Rb)
+template <int K0, int K1, class SH>
+__device__ __forceinline__ void tc16_rback(const Tc16Ctx<SH>& c, int kb, const float (&yA)[4], const float (&yB)[4], const float (&RbA)[10],
+                                           const float (&RbB)[10], float2 (&XA)[4], float2 (&XB)[4]) {
+    const float4* F = c.fields();
+#pragma unroll
+    for (int k = K0; k < K1; ++k) {
+        const int P = tc16_pair(c, kb, k);
+        float2 rbA, rbB;
+        {
+            const float4 cc = F[7 * SH::NP + P];
+            rbA = fma2(zw(cc), bc2(RbA[1]), mul2(xy(cc), bc2(RbA[0])));
+            rbB = fma2(zw(cc), bc2(RbB[1]), mul2(xy(cc), bc2(RbB[0])));
+        }
+#pragma unroll
+        for (int j = 1; j < 5; ++j) {
+            const float4 cc = F[(7 + j) * SH::NP + P];
+            rbA = fma2(xy(cc), bc2(RbA[2 * j]), rbA);
+            rbA = fma2(zw(cc), bc2(RbA[2 * j + 1]), rbA);
+            rbB = fma2(xy(cc), bc2(RbB[2 * j]), rbB);
+            rbB = fma2(zw(cc), bc2(RbB[2 * j + 1]), rbB);
+        }
+        const float4 u01 = F[5 * SH::NP + P], u23 = F[6 * SH::NP + P];
+        const float2 br1 = zw(F[2 * SH::NP + P]);
+        const float2 rA = tanh_tc2(pair_affine(u01, u23, yA, br1));
+        const float2 rB = tanh_tc2(pair_affine(u01, u23, yB, br1));
+        pair_scatter(u01, u23, mul2(rbA, one_minus_sq(rA)), XA);
+        pair_scatter(u01, u23, mul2(rbB, one_minus_sq(rB)), XB);
+        sched_fence();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// xbar = (df/dy)^T v, ubar = (df/du)^T v from the taped activations of the forward evaluation at the same stage state
+// and the Hessian-vector product of H_net.  Products: dz2 = W2 da1, dg1 = W2^T e2.
+// ---------------------------------------------------------------------------------------
+template <class SH>
+__device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u,
+                                              const float (&v)[4], float (&xbar)[4], float& ubar) {
+    constexpr int NKB = SH::NKB, NP = SH::NP;
+    const float4* F = c.fields();
+    float z[4], w[4], G4[4], sv[4], Rb[10];
+    Canon cq = {};
+    float pb[2] = {0.f, 0.f}, pdb[2] = {0.f, 0.f};
+    // first tape blocks of the da1 loop, requested before the per-instance algebra below
+    float4 an[4], gn[4];
+    c.template tape_load<false>(1, 0, an);
+    c.template tape_load<true>(2, 0, gn);
+    // grad H of the forward evaluation at this stage state (ld.cg: written by the co-owner lane)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) G4[i] = __ldcg(c.sck + ((size_t)c.ev * 16 + 10 + i) * 128 + c.row);
+    if constexpr (SH::MK == MK_CANON) {
+        cq = canon_of(p, y[1]);
+        z[0] = y[0]; z[1] = y[1];
+        z[2] = p.ma * y[2] + cq.beta * y[3];
+        z[3] = cq.beta * y[2] + p.mc * y[3];
+        pb[0] = cq.n11 * v[0] + cq.n12 * v[1];
+        pb[1] = cq.n12 * v[0] + cq.n22 * v[1];
+        pdb[0] = cq.n11 * v[2] + cq.n12 * v[3];
+        pdb[1] = cq.n12 * v[2] + cq.n22 * v[3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // w = (J - diag r)^T [0, 0, pdb]
+            float s = 0.f;
+#pragma unroll
+            for (int r = 2; r < 4; ++r) s = fmaf(p.Jm[r * 4 + k] - (r == k ? p.rdiag[r] : 0.f), pdb[r - 2], s);
+            w[k] = s;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z[i] = y[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) Rb[i] = 0.f;
+    if constexpr (SH::HAS_R) {
+        float Sp[12], S[4][4], tg[4];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) Sp[i] = __ldcg(c.sck + ((size_t)c.ev * 16 + i) * 128 + c.row);
+        tc_make_S(p, Sp, S);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) sv[a] = fmaf(S[a][3], v[3], fmaf(S[a][2], v[2], fmaf(S[a][1], v[1], S[a][0] * v[0])));
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {  // w = (J - J^T)^T v - S (S v)
+            float s = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) s = fmaf(p.Jm[b * 4 + a], v[b], s);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) s = fmaf(-S[a][b], sv[b], s);
+            w[a] = s;
+        }
+        // cotangent of S: -(v t^T + g s^T) symmetrised, packed with multiplicity 2 off the diagonal
+#pragma unroll
+        for (int a = 0; a < 4; ++a) tg[a] = fmaf(S[a][3], G4[3], fmaf(S[a][2], G4[2], fmaf(S[a][1], G4[1], S[a][0] * G4[0])));
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b)
+                Rb[sym_idx(a, b)] = (a == b ? -0.5f : -1.0f) * (v[a] * tg[b] + G4[a] * sv[b] + v[b] * tg[a] + G4[b] * sv[a]);
+    }
+    // One exact power-of-two scale per instance and evaluation brings the cotangent into the FP16 window of the
+    // adjoint products (max |w'| in [2^wexp, 2^(wexp+1))): everything below is linear in (w, Rb), the result is
+    // multiplied by 1 / scale at the end -- bit-identical FP32 arithmetic on the element side.
+    float isc;
+    {
+        const float mu = fmaxf(fmaxf(fabsf(w[0]), fabsf(w[1])), fmaxf(fabsf(w[2]), fabsf(w[3])));
+        int se = p.wexp16 + 254 - (int)((__float_as_uint(mu) >> 23) & 0xffu);
+        se = mu > 0.f ? min(max(se, 1), 253) : 127;
+        const float sc = __uint_as_float((uint32_t)se << 23);
+        isc = __uint_as_float((uint32_t)(254 - se) << 23);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] *= sc;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) Rb[i] *= sc;
+    }
+    float wA[4], wB[4], yA[4], yB[4], RbA[10], RbB[10];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { wA[i] = c.fromA(w[i]); wB[i] = c.fromB(w[i]); }
+    if constexpr (SH::HAS_R) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { yA[i] = c.fromA(y[i]); yB[i] = c.fromB(y[i]); }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { RbA[i] = c.fromA(Rb[i]); RbB[i] = c.fromB(Rb[i]); }
+    }
+    // xbar partials over my hidden units as (even, odd) pairs: X from the R_net chain and the dg1 half of xbar_H,
+    // T the g1 half of xbar_H without its factor -2
+    float2 XA[4], XB[4], TA[4], TB[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { XA[i] = XB[i] = TA[i] = TB[i] = make_float2(0.f, 0.f); }
+    // ---- A3: da1 = s1 * (W1 w) -> operand A of product 1 (dz2 = W2 da1), with the g1 half of xbar_H (sdot1 * g1) and
+    //      half of the R_net chain in the same loop ----
+    {
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) {
+            float4 ac[4], gc[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { ac[s] = an[s]; gc[s] = gn[s]; }
+            if (kb + 1 < NKB) {
+                c.template tape_load<false>(1, kb + 1, an);
+                c.template tape_load<true>(2, kb + 1, gn);
+            }
+            float2 da[2][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int P = tc16_pair(c, kb, k);
+                const float4 w01 = F[P], w23 = F[NP + P];
+                {
+                    const float2 a1 = tape_pair(ac, 0, k);
+                    da[0][k] = mul2(one_minus_sq(a1), pair_linear(w01, w23, wA));
+                    pair_scatter(w01, w23, mul2(mul2(a1, da[0][k]), tape_pair(gc, 0, k)), TA);
+                }
+                {
+                    const float2 a1 = tape_pair(ac, 1, k);
+                    da[1][k] = mul2(one_minus_sq(a1), pair_linear(w01, w23, wB));
+                    pair_scatter(w01, w23, mul2(mul2(a1, da[1][k]), tape_pair(gc, 1, k)), TB);
+                }
+            }
+            c.put_block(kb, da, 1.0f);
+            if constexpr (SH::HAS_R) {
+                if (kb >= PHNN_TC_RSKEW) tc16_rback<0, 2>(c, kb - PHNN_TC_RSKEW, yA, yB, RbA, RbB, XA, XB);
+            }
+        }
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rback<0, 2>(c, kb, yA, yB, RbA, RbB, XA, XB);
+        }
+        c.end_feed();
+    }
+    // ---- B3: e2 = -2 a2 da2 w3 -> operand A of product 2 (dg1 = W2^T e2), in place; the rest of the R_net chain ----
+    {
+        float4 a2n[4];
+        c.template tape_load<true>(0, 0, a2n);
+        const uint32_t tacc = c.acc_wait();
+        const float isb = p.s16[2];
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dz)[16]) {
+            float4 a2q[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) a2q[s] = a2n[s];
+            if (kb + 1 < NKB) c.template tape_load<true>(0, kb + 1, a2n);
+            float2 e2[2][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 m2w3 = xy(F[4 * NP + tc16_pair(c, kb, k)]);  // -2 w3 * S_e pair
+#pragma unroll
+                for (int rsel = 0; rsel < 2; ++rsel) {
+                    const float2 a2 = tape_pair(a2q, rsel, k);
+                    const float2 dzz = mul2(frag2(dz, k, rsel), bc2(isb));
+                    e2[rsel][k] = mul2(mul2(a2, mul2(one_minus_sq(a2), dzz)), m2w3);
+                }
+            }
+            c.put_block(kb, e2, 1.0f);
+            if constexpr (SH::HAS_R) {
+                if (kb >= PHNN_TC_RSKEW) tc16_rback<2, 4>(c, kb - PHNN_TC_RSKEW, yA, yB, RbA, RbB, XA, XB);
+            }
+        });
+        if constexpr (SH::HAS_R) {
+#pragma unroll
+            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rback<2, 4>(c, kb, yA, yB, RbA, RbB, XA, XB);
+        }
+        c.end_feed();
+    }
+    // ---- C4: the dg1 half of xbar_H ----
+    {
+        float4 a1n[4];
+        c.template tape_load<true>(1, 0, a1n);
+        const uint32_t tacc = c.acc_wait();
+        const float isd = p.s16[3];
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dg)[16]) {
+            float4 ac[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) ac[s] = a1n[s];
+            if (kb + 1 < NKB) c.template tape_load<true>(1, kb + 1, a1n);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int P = tc16_pair(c, kb, k);
+                const float4 w01 = F[P], w23 = F[NP + P];
+                pair_scatter(w01, w23, mul2(one_minus_sq(tape_pair(ac, 0, k)), mul2(frag2(dg, k, 0), bc2(isd))), XA);
+                pair_scatter(w01, w23, mul2(one_minus_sq(tape_pair(ac, 1, k)), mul2(frag2(dg, k, 1), bc2(isd))), XB);
+            }
+        });
+        tc_fence_before();
+    }
+    float X4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        X4[i] = c.quad_own_sum(fmaf(-2.f, TA[i].x + TA[i].y, XA[i].x + XA[i].y), fmaf(-2.f, TB[i].x + TB[i].y, XB[i].x + XB[i].y)) * isc;
+    if constexpr (SH::MK == MK_CANON) {
+        // chain through z = [q, M(theta) qdot] and M^-1(theta) (src/mass_matrix.py:310-362), SURVEY.md Appendix A
+        float pd[2];
+        tc_canon_pdot(p, G4, u, pd);
+        const float dbeta = -p.mb * cq.sth;
+        const float dD = -2.f * cq.beta * dbeta;
+        const float iD2 = 1.f / (cq.D * cq.D);
+        const float dn11 = -p.mc * iD2 * dD;
+        const float dn12 = -dbeta / cq.D + cq.beta * iD2 * dD;
+        const float dn22 = -p.ma * iD2 * dD;
+        float thbar = v[0] * (dn11 * z[2] + dn12 * z[3]) + v[1] * (dn12 * z[2] + dn22 * z[3]);
+        thbar += v[2] * (dn11 * pd[0] + dn12 * pd[1]) + v[3] * (dn12 * pd[0] + dn22 * pd[1]);
+        float zb[4] = {X4[0], X4[1], X4[2] + pb[0], X4[3] + pb[1]};
+        thbar += dbeta * (zb[2] * y[3] + zb[3] * y[2]);
+        xbar[0] = zb[0];
+        xbar[1] = zb[1] + thbar;
+        xbar[2] = p.ma * zb[2] + cq.beta * zb[3];
+        xbar[3] = cq.beta * zb[2] + p.mc * zb[3];
+        ubar = p.Gv[2] * pdb[0] + p.Gv[3] * pdb[1];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xbar[i] = X4[i];
+        ubar = fmaf(p.Gv[3], v[3], fmaf(p.Gv[2], v[2], fmaf(p.Gv[1], v[1], p.Gv[0] * v[0])));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------
+template <int MK, int NS, int HID>
+__global__ void __launch_bounds__(Tc16Shape<MK, NS, HID>::THREADS, 1) phnn_tc16_kernel(const __grid_constant__ KParams p) {
+    using SH = Tc16Shape<MK, NS, HID>;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 512);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int e = 0; e < SH::NKB; ++e) mbar_init(&bars[SH::B_AFULL + e], SH::NEW);
+        for (int e = 0; e < SH::NBE; ++e) {
+            mbar_init(&bars[SH::B_BFULL + e], 1);
+            mbar_init(&bars[SH::B_BEMPTY + e], 1);
+        }
+        mbar_init(&bars[SH::B_ACC + 0], 1);
+        mbar_init(&bars[SH::B_ACC + 1], 1);
+        mbar_init(&bars[SH::B_SMALL], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == SH::NEW) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"((uint32_t)SH::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_ptr;
+
+    // evaluation schedule (same derivation as phnn_kernel)
+    const int E = p.T * p.S;
+    int n_outer = 1, nfwd = 0, nadj = 0;
+    switch (p.mode) {
+        case MODE_FORWARD: nfwd = 1; break;
+        case MODE_VJP: nadj = 1; break;
+        case MODE_ROLLOUT: nfwd = E + (p.energy_mode == 2 ? 1 : 0); break;
+        case MODE_COSTGRAD: nfwd = E; nadj = p.want_grad ? E : 0; break;
+        default: n_outer = p.iters; nfwd = E; nadj = E; break;
+    }
+    const bool steal = (p.mode == MODE_SOLVE) && p.sched != nullptr && p.iters > 0;
+    const long long nprod = (steal ? 1LL : (long long)n_outer) * (2LL * nfwd + 2LL * nadj);
+    const long long per_iter = 2LL * nfwd + 2LL * nadj;
+    const long long my_tiles = p.tiles > (long long)blockIdx.x ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const size_t tape_eval = (size_t)3 * HID * 128;  // floats per taped evaluation
+    float* const tape = (p.tape && nadj > 0) ? p.tape + (size_t)blockIdx.x * E * tape_eval : nullptr;
+    StealSched ss{p.sched, p.sched + 1, p.tiles, p.iters, reinterpret_cast<int*>(phnn_smem + 768), 32 * SH::NEW};
+
+    if (warp < SH::NEW) {
+        // ===== element threads =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SH::REGS_ELEM));
+        Tc16Ctx<SH> c;
+        const int quad = warp & 3, half = warp >> 2, g = lane >> 2;
+        c.lane = lane;
+        c.cq = lane & 3;
+        c.srcA = lane & ~3;
+        c.srcB = (lane & ~3) | 2;
+        c.row = quad * 32 + half * 16 + g + 8 * ((lane >> 1) & 1);
+        c.tid = threadIdx.x;
+        c.tl16 = tbase + ((uint32_t)(quad * 32 + half * 16) << 16);
+        c.qdone = 0;
+        c.qfeed = 0;
+        c.store = (lane & 1) == 0;
+        c.tape = tape;
+        c.sck = nullptr;
+        c.ev = 0;
+        mbar_wait(&bars[SH::B_SMALL], 0);
+        if (steal) {
+            run_job(c, p, ss, c.row);
+        } else {
+            StridedSched sched{(long long)blockIdx.x, (long long)blockIdx.x, p.tiles, (int)gridDim.x, n_outer, 0};
+            run_job(c, p, sched, c.row);
+        }
+        tc_fence_before();
+    } else if (warp == SH::NEW) {
+        // ===== MMA issuer =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SH::REGS_AUX));
+        const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // F16 x F16 -> F32
+        const uint32_t b_base = smem_u32(phnn_smem + SH::OFF_B);
+        uint32_t bent = 0;
+        long long qtot = 0;  // products issued so far (accumulator / operand parity continues across units)
+        for (long long unit = 0;; ++unit) {
+            if (steal ? ss.grab() < 0 : unit >= my_tiles) break;
+            if (lane == 0) {
+#pragma unroll 1
+                for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
+                    const uint32_t par = (uint32_t)(qtot & 1);
+                    const uint32_t acc = tbase + par * HID;
+                    const uint32_t afeed = tbase + (par ^ 1u) * HID;
+#pragma unroll 1
+                    for (int kb = 0; kb < SH::NKB; ++kb) {
+                        mbar_wait_sleep(&bars[SH::B_AFULL + kb], par, PHNN_TC_MMA_SLEEP);
+                        const uint32_t e = bent % SH::NBE;
+                        mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, PHNN_TC_MMA_SLEEP);
+                        tc_fence_after();
+                        const uint32_t b_t = b_base + e * SH::B_TILE;
+                        const uint32_t a_hi = afeed + kb * 32, a_lo = a_hi + 16;
+                        // a_hi b_hi + a_hi b_lo + a_lo b_hi; the weight row is [b_hi (64 B) | b_lo (64 B)], K = 16 per MMA
+                        umma_f16_ts(acc, a_hi, umma_desc_sw128(b_t), idesc, kb ? 1u : 0u);
+                        umma_f16_ts(acc, a_hi + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
+                        umma_f16_ts(acc, a_hi, umma_desc_sw128(b_t + 64), idesc, 1u);
+                        umma_f16_ts(acc, a_hi + 8, umma_desc_sw128(b_t + 96), idesc, 1u);
+                        umma_f16_ts(acc, a_lo, umma_desc_sw128(b_t), idesc, 1u);
+                        umma_f16_ts(acc, a_lo + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
+                        umma_commit(&bars[SH::B_BEMPTY + e]);
+                        ++bent;
+                    }
+                    umma_commit(&bars[SH::B_ACC + par]);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp > SH::NEW + 1) {
+        // ===== idle warps of the auxiliary warpgroup: give their registers away, keep the CTA-wide barriers company =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SH::REGS_AUX));
+        for (long long unit = 0;; ++unit)
+            if (steal ? ss.grab() < 0 : true) break;
+    } else {
+        // ===== weight producer (bulk copies of pre-swizzled K-blocks) + L2 prefetch of the tape =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SH::REGS_AUX));
+        if (lane == 0) {
+            mbar_expect_tx(&bars[SH::B_SMALL], SH::SMALL * 4);
+            bulk_g2s(phnn_smem + SH::OFF_SMALL, p.wsmall16, SH::SMALL * 4, &bars[SH::B_SMALL]);
+        }
+        uint32_t bent = 0;
+        long long qtot = 0;
+        for (long long unit = 0;; ++unit) {
+            if (steal ? ss.grab() < 0 : unit >= my_tiles) break;
+            if (lane == 0) {
+#pragma unroll 1
+                for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
+                    // adjoint products of evaluation e (descending): 0 -> da1 loop (reads a1, g1), 1 -> e2 loop (reads a2)
+                    const long long qi = tape ? qq % per_iter - 2LL * nfwd : -1;
+                    const unsigned char* src = p.wtc16 + (size_t)(qtot & 1) * SH::NKB * SH::B_TILE;
+#pragma unroll 1
+                    for (int kb = 0; kb < SH::NKB; ++kb) {
+                        if (qi >= 0) {
+                            // pull the tape blocks the element threads will read PF_AHEAD K-block steps from now into L2
+                            constexpr int PF_AHEAD = PHNN_TC_PF_AHEAD;
+                            int step = (int)(qi & 1) * SH::NKB + kb + PF_AHEAD;
+                            long long te = (long long)E - 1 - (qi >> 1);
+                            if (step >= 2 * SH::NKB) { step -= 2 * SH::NKB; --te; }
+                            if (te >= 0) {
+                                const float* ev0 = tape + (size_t)te * tape_eval;
+                                constexpr size_t ARR = (size_t)HID * 128, BLK = 4096;  // floats per array / per K-block
+                                if (step < SH::NKB) {
+                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ev0 + ARR + step * BLK), "r"(16384) : "memory");
+                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ev0 + 2 * ARR + step * BLK), "r"(16384) : "memory");
+                                } else {
+                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ev0 + (step - SH::NKB) * BLK), "r"(16384) : "memory");
+                                }
+                            }
+                        }
+                        const uint32_t e = bent % SH::NBE;
+                        mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, PHNN_TC_PROD_SLEEP);
+                        mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
+                        bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)kb * SH::B_TILE, SH::B_TILE, &bars[SH::B_BFULL + e]);
+                        ++bent;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == SH::NEW) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"((uint32_t)SH::TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace phnn

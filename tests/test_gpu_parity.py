@@ -251,7 +251,7 @@ def tc_env(env):
 
 
 @pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256", "canonical"])
-@pytest.mark.parametrize("mode", [3, 2, 1])
+@pytest.mark.parametrize("mode", [4, 3, 2, 1])
 def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
     # modes 3 (3xTF32) and 2 (TF32 + BF16 correction product) are held to the FP32 tolerances, mode 1 (plain TF32) to its own
     ops, get_tc = tc_env
@@ -457,7 +457,7 @@ def test_lat_stacked_instances_vs_oracle(lat_env, name, B):
 # ---------------------------------------------------------------------------------------------
 # BASELINE cfg5 horizons and full-size properties
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [4, 2, 3])
 @pytest.mark.parametrize("H", [100, 200])
 def test_tc_long_horizons_vs_oracle(tc_env, H, mode):
     """cfg5 horizons (RK4, h=256) on a 128-instance sub-sample against the CPU oracle: cost, dJ/dU, two Adam steps;
@@ -585,7 +585,7 @@ def test_workspace_contract(tc_env):
     assert b"workspace too small" in L.phnn_last_error()
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [4, 2, 3])
 def test_tc_wide_states_and_saturated_units(tc_env, mode):
     """the tensor-core schemes at the edge of their operand range: states over the range of the reference's training
     data (|x| up to ~20: most tanh units saturate, so a1 is +-1 and delta2 / s1 are tiny) - forward against the golden
@@ -624,7 +624,7 @@ def _cfg4_cost():
     return Q, R, ca
 
 
-@pytest.mark.parametrize("mode", [2])
+@pytest.mark.parametrize("mode", [4, 2])
 def test_benchmarked_config_vs_oracle(tc_env, mode):
     """bench.py's default job on 256 of its own instances (the first 256 of rank 0): tensor_mode 2, hidden 256, H=50,
     RK4, 20 Adam iterations, cold start -- cost history, dJ/dU at iteration 0 and at iteration 19, final controls,
@@ -657,7 +657,7 @@ def test_benchmarked_config_vs_oracle(tc_env, mode):
     assert rel_err(c19.cpu().numpy(), histo[iters - 1]) < HORIZON_TOL   # and it is the 20th entry of the history
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [4, 2, 3])
 def test_cfg4_shape_golden_reference(tc_env, mode):
     """the same job on 64 instances against the fixture recorded from the REFERENCE ITSELF (one hop, no oracle):
     tests/golden/cfg4_shape.npz = make_golden.gen_cfg4_shape (reference PyTorch autograd + torch.optim.Adam)."""
