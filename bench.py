@@ -250,7 +250,8 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU time for the whole reference arm")
     ap.add_argument("--ref-batch", type=int, default=0, help="reference arm: instances per step (default: sized to --ref-budget)")
     ap.add_argument("--tensor-mode", type=int, default=-1,
-                    help="0 FP32-FMA kernel, 2 tcgen05 TF32 + BF16 correction product (default), 3 tcgen05 3xTF32, 1 tcgen05 plain TF32")
+                    help="0 FP32-FMA kernel, 4 tcgen05 3 x FP16 hi/lo products with A in TMEM (default), 2 tcgen05 TF32 + BF16 "
+                         "correction product, 3 tcgen05 3xTF32, 1 tcgen05 plain TF32")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.batch:
@@ -432,7 +433,7 @@ def main():
     # ---- side measurement: plain TF32 (tensor_mode 1), the looser stated-tolerance path north_star permits ----
     alt = None
     tmode = pk.get_option("tensor_mode")
-    uses_tc = tmode in (1, 2, 3) and B >= pk.get_option("tensor_min_batch")
+    uses_tc = tmode in (1, 2, 3, 4) and B >= pk.get_option("tensor_min_batch")
     if uses_tc and tmode != 1 and not args.no_alt:
         pk.set_option("tensor_mode", 1)
         for _ in range(2):
@@ -517,11 +518,14 @@ def main():
         # mode 1 as 1 TF32 MMA.  BF16 MMAs run at twice the TF32 rate, so the time at peak rate is counted in TF32 units.
         tiles = (B + 127) // 128
         base = tiles * iters * H * S * (2 + 2) * 2.0 * 128 * h * h
-        tf32_flops = base * (3 if tmode == 3 else 1)
-        bf16_flops = base * 2 if tmode == 2 else 0.0
+        tf32_flops = base * (3 if tmode == 3 else 1) if tmode != 4 else 0.0
+        # 16-bit MMAs (twice the TF32 rate): mode 2 one BF16 product of twice the depth; mode 4 three FP16 products
+        # (a_hi b_hi + a_hi b_lo + a_lo b_hi), operand A read from tensor memory
+        bf16_flops = base * 2 if tmode == 2 else (base * 3 if tmode == 4 else 0.0)
         mma_flops = tf32_flops + bf16_flops
         tf32_equiv_flops = tf32_flops + bf16_flops / 2
-        scheme = {3: "3xTF32 error-compensated", 2: "TF32 + BF16 correction product (FP32-level accuracy)", 1: "plain TF32"}[tmode]
+        scheme = {4: "3 x FP16 hi/lo products, A in TMEM (FP32-level accuracy)", 3: "3xTF32 error-compensated",
+                  2: "TF32 + BF16 correction product (FP32-level accuracy)", 1: "plain TF32"}[tmode]
         # HBM side of the same kernel: the activation tape (a1, a2, g1: 3 h floats per instance and evaluation) is
         # written by the forward sweep and read back by the adjoint
         tape_bytes = tiles * iters * H * S * 2.0 * 3 * h * 128 * 4
@@ -531,8 +535,9 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, this pool)" if peaks else
                                    "fallback 1400 (B200_PROFILING.md)",
                     "algorithmic_flops_per_launch": algo,
-                    "kernel": "phnn_tc_kernel<MK,NS,HID> (tcgen05 kind::tf32%s, %s), one launch per step" % (
-                        " + kind::f16" if tmode == 2 else "", scheme),
+                    "kernel": ("phnn_tc16_kernel<MK,NS,HID> (tcgen05 kind::f16, %s), one launch per step" % scheme) if tmode == 4 else
+                              "phnn_tc_kernel<MK,NS,HID> (tcgen05 kind::tf32%s, %s), one launch per step" % (
+                                  " + kind::f16" if tmode == 2 else "", scheme),
                     "kernel_ms": kernel_ms,
                     "executed_tensor_tflops": mma_flops / (kernel_ms * 1e-3) / 1e12,
                     "tf32_mma_peak_tflops": tf32_peak,
@@ -543,10 +548,12 @@ def main():
                             "achieved_gbps": tape_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbps": hbm_peak,
                             "frac": tape_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                             "measured_dram_bytes_per_launch": traffic},
-                    "note": "FP32-level accuracy on the tensor cores costs one TF32 product (half the bf16 rate) plus a BF16 "
-                            "correction product of twice the depth: frac vs the bf16 peak is bounded by 1/4; the adjoint "
-                            "reads the forward activations from an HBM tape instead of recomputing them (4 tensor products "
-                            "per pair instead of 6)"}
+                    "note": ("FP32-level accuracy on the tensor cores costs three FP16 products per algorithmic product (hi/lo "
+                             "split operands): frac vs the bf16 peak is bounded by 1/3; " if tmode == 4 else
+                             "FP32-level accuracy on the tensor cores costs one TF32 product (half the bf16 rate) plus a BF16 "
+                             "correction product of twice the depth: frac vs the bf16 peak is bounded by 1/4; ") +
+                            "the adjoint reads the forward activations from an HBM tape instead of recomputing them (4 tensor "
+                            "products per pair instead of 6)"}
     else:
         roofline = {"bound": "fp32-fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak, "traffic": traffic,
@@ -602,7 +609,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
-            "kernel_path": {3: "tcgen05-3xTF32", 2: "tcgen05-TF32+BF16corr", 1: "tcgen05-TF32"}[tmode] if uses_tc else "fp32-fma",
+            "kernel_path": {4: "tcgen05-3xFP16-A-in-TMEM", 3: "tcgen05-3xTF32", 2: "tcgen05-TF32+BF16corr", 1: "tcgen05-TF32"}[tmode] if uses_tc else "fp32-fma",
             "exchange": {"kind": gather_kind, "ms": gather_ms,
                          "note": "issued once per step, inside every timed step; `ms` is the exchange alone, warmed, median of 7"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps,

@@ -425,7 +425,9 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         pk->base.s16[4] = pow2f(sc.eA);
         pk->base.s16[5] = pow2f(-sc.eD);
         pk->base.wexp16 = sc.wexp;
-        pk->tc_mode = 2;  // TF32 + BF16 correction product: FP32-level accuracy at 2/3 of the MMA work of 3xTF32
+        // default: the second-generation kernel (three FP16 products, operand A in tensor memory): FP32-level accuracy,
+        // measured 1.2-1.3x the first-generation kernel's default (mode 2: TF32 + BF16 correction product)
+        pk->tc_mode = 4;
         pk->tc_min_batch = 1;  // measured: the tcgen05 kernel beats the FP32-FMA kernel at every batch size (tools/gpu_crossover.py)
     }
     cudaSetDevice(prev);
@@ -560,23 +562,30 @@ static int launch_lat_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream
     return 0;
 }
 
-// Workspace of a job with an adjoint on the tcgen05 kernel (floats unless noted):
-//   [tiles x ws_floats_per_tile(.., tc_ws_extra)]  stage states, Adam moments, best controls, R_net sums / grad H
-//   [tiles + 4 ints, padded to 16 bytes]            work-stealing scheduler words
+// Workspace of a job with an adjoint on the tcgen05 kernels (floats unless noted):
+//   [tiles x 128 x (3 T + 1)]                       what outlives a (tile, iteration) unit: Adam moments, best controls, best cost
+//   [tiles + 4 ints, padded to 128 bytes]           work-stealing scheduler words
 //   [grid x T*S x 3 x h x 128]                      activation tape, one region per CTA (grid = min(tiles, SMs))
+//   [grid x T*S x (n + 16) x 128]                   per-CTA stage states + R_net sums / grad H of the unit in flight
 struct TcWorkspace {
-    size_t tile_floats, sched_off, tape_off, bytes;
+    size_t tile_floats, sched_off, tape_off, scratch_off, bytes;
     long long tiles, grid;
 };
 static TcWorkspace tc_workspace(const phnn_pack* pk, long long B, int T, int S) {
     TcWorkspace w;
     w.tiles = (B + 127) / 128;
     w.grid = w.tiles < pk->num_sms ? w.tiles : pk->num_sms;
-    w.tile_floats = ws_floats_per_tile(pk->n, T, S, 128, tc_ws_extra(pk->h, T, S));
+    w.tile_floats = ws_persist_floats_per_tile(T, 128);
     w.sched_off = (size_t)w.tiles * w.tile_floats * sizeof(float);
     w.tape_off = (w.sched_off + sizeof(int) * (size_t)(w.tiles + 4) + 127) / 128 * 128;
-    w.bytes = w.tape_off + (size_t)w.grid * T * S * 3 * pk->h * 128 * sizeof(float);
+    w.scratch_off = w.tape_off + (size_t)w.grid * T * S * 3 * pk->h * 128 * sizeof(float);
+    w.bytes = w.scratch_off + (size_t)w.grid * tc_scratch_floats_per_cta(pk->n, T, S) * sizeof(float);
     return w;
+}
+// the FP32-FMA kernel (32-instance tiles) and the latency kernel (single-instance tiles) keep the stage states per tile
+static size_t fp32_workspace_bytes(const phnn_pack* pk, long long B, int T, int S) {
+    const size_t inst = (size_t)((B + 31) / 32) * 32;
+    return (inst * ((size_t)T * S * pk->n + 3 * (size_t)T + 1) * sizeof(float) + 127) / 128 * 128;
 }
 
 template <class SH>
@@ -596,6 +605,7 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     P.tiles = tiles;
     P.sched = nullptr;
     P.tape = nullptr;
+    P.scratch = nullptr;
     long long grid = tiles;
 #ifdef PHNN_TC_PROFILE
     static const bool no_steal = getenv("PHNN_NO_STEAL") != nullptr;  // experiment switch (profiling builds only)
@@ -610,6 +620,7 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
         const TcWorkspace w = tc_workspace(pk, P.B, P.T, P.S);
         grid = w.grid;
         P.tape = reinterpret_cast<float*>(reinterpret_cast<char*>(P.ws) + w.tape_off);
+        P.scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(P.ws) + w.scratch_off);
         if (P.mode == MODE_SOLVE && !no_steal) {
             P.sched = reinterpret_cast<int*>(reinterpret_cast<char*>(P.ws) + w.sched_off);
             CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
@@ -730,13 +741,11 @@ extern "C" int phnn_rollout(const phnn_pack* pk, const float* x0, const float* U
 extern "C" size_t phnn_workspace_bytes(const phnn_pack* pk, long B, int T, int integrator) {
     if (!pk || B <= 0 || T <= 0) return 0;
     const int S = integrator == PHNN_RK4 ? 4 : 1;
-    // the tcgen05 kernel's layout (128-instance tiles + scheduler words + activation tape) when this batch is
-    // routed there; otherwise the per-tile part alone, a superset of what the 32-instance tiles of the FP32
-    // kernel and the single-instance tiles of the latency kernel use
+    // the tcgen05 kernels' layout when this batch is routed there, otherwise the per-tile layout of the FP32-FMA /
+    // latency kernels
     const bool lat = pk->lat_max_batch > 0 && B <= pk->lat_max_batch && has_lat_shape(pk->mk, pk->n, pk->h);
     const bool tc = !lat && pk->tc_mode != 0 && pk->d_wtc && B >= pk->tc_min_batch;
-    const TcWorkspace w = tc_workspace(pk, B, T, S);
-    return tc ? w.bytes : w.tape_off;
+    return tc ? tc_workspace(pk, B, T, S).bytes : fp32_workspace_bytes(pk, B, T, S);
 }
 
 extern "C" int phnn_cost_grad(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, const float* U,

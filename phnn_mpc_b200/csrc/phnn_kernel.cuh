@@ -122,6 +122,8 @@ struct KParams {
     int* sched;        // work-stealing solve (tcgen05 kernel): [0] unit counter, [1 + tile] iterations completed
     long long tiles;   // number of 128-instance tiles (tcgen05 kernel)
     float* tape;       // tcgen05 kernel: activation tape, [grid][T*S][3][h][128] floats (jobs with an adjoint)
+    float* scratch;    // tcgen05 kernels: per-CTA stage states [T*S][n][128] + R_net sums / grad H [T*S][16][128] of the
+                       // (tile, iteration) unit in flight; nullptr: the stage states live in the tile's workspace
     long long* dbg;    // optional profiling output (PHNN_TC_PROFILE builds)
 };
 
@@ -136,6 +138,11 @@ __host__ __device__ inline size_t ws_floats_per_tile(int NS, int T, int S, int T
 // extra workspace floats per instance of the tcgen05 kernel: 16 per evaluation for the symmetrised R_net sums
 // (10) and grad H (4) the forward sweep leaves for the adjoint
 __host__ __device__ inline int tc_ws_extra(int /*h*/, int T, int S) { return 16 * T * S; }
+// What has to outlive a (tile, iteration) unit: Adam m, v, best controls [T][TW] and the best cost [TW].  The
+// tcgen05 kernels keep only this per tile; stage states, R_net sums and grad H are consumed by the reverse sweep of the
+// same unit and live in a per-CTA scratch region (KParams::scratch), so 1 M instances x H = 200 fit one GPU.
+__host__ __device__ inline size_t ws_persist_floats_per_tile(int T, int TW) { return (size_t)TW * (3 * (size_t)T + 1); }
+__host__ __device__ inline size_t tc_scratch_floats_per_cta(int NS, int T, int S) { return (size_t)T * S * (NS + 16) * 128; }
 
 // One unit of work of a job: iteration `it` (1-based) of tile `tile`.  The static schedule hands a
 // CTA the iterations of its own tile in order; the work-stealing schedule of the tcgen05 kernel
@@ -300,6 +307,7 @@ struct Ctx {
     __device__ __forceinline__ int kown(int o) const { return wcol + ((o >> 2) << 5) + (o & 3); }
     __device__ __forceinline__ float* row_own(float* buf, int k) const { return buf + k * GI + (chunk << 3); }
     __device__ __forceinline__ void begin_unit(const KParams&, long long) {}
+    __device__ __forceinline__ float* unit_scratch() const { return nullptr; }
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
         phnn::eval_fwd(*this, p, y, u, f, H);
     }
@@ -993,10 +1001,12 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
 #pragma unroll
     for (int i = 0; i < NS; ++i) x0[i] = valid ? p.x0[b * NS + i] : 0.f;
 
-    // workspace of this tile: stage states [E][NS][TW], Adam m/v and best controls [T][TW]
-    float* wsg = p.ws ? p.ws + (size_t)tile * ws_floats_per_tile(NS, T, S, TW, ENG::ws_extra(p)) : nullptr;
-    float* ckpt = wsg;
-    float* adam_m = wsg ? wsg + (size_t)E * NS * TW : nullptr;
+    // workspace of this tile: stage states [E][NS][TW] (or the engine's per-CTA scratch), Adam m/v and best controls [T][TW]
+    float* const scratch = c.unit_scratch();
+    const size_t tile_floats = scratch ? ws_persist_floats_per_tile(T, TW) : ws_floats_per_tile(NS, T, S, TW, ENG::ws_extra(p));
+    float* wsg = p.ws ? p.ws + (size_t)tile * tile_floats : nullptr;
+    float* ckpt = scratch ? scratch : wsg;
+    float* adam_m = wsg ? wsg + (scratch ? (size_t)0 : (size_t)E * NS * TW) : nullptr;
     float* adam_v = adam_m ? adam_m + (size_t)T * TW : nullptr;
     float* ubest = adam_v ? adam_v + (size_t)T * TW : nullptr;
     float* bestws = ubest ? ubest + (size_t)T * TW : nullptr;

@@ -393,9 +393,10 @@ struct TcCtx {
         }
         gbar();
     }
-    __device__ __forceinline__ void begin_unit(const KParams& p, long long tile) {
-        const size_t tile_floats = ws_floats_per_tile(NS, p.T, p.S, TW, ws_extra(p));
-        sck = p.ws ? p.ws + (size_t)tile * tile_floats + ws_floats_per_tile(NS, p.T, p.S, TW, 0) : nullptr;
+    float* scratch;  // per-CTA stage states + R_net sums / grad H of the unit in flight (nullptr: no adjoint follows)
+    __device__ __forceinline__ float* unit_scratch() const { return scratch; }
+    __device__ __forceinline__ void begin_unit(const KParams& p, long long) {
+        sck = scratch ? scratch + (size_t)p.T * p.S * NS * TW : nullptr;
     }
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[4], float u, float (&f)[4], float& H) {
         tc_eval_fwd(*this, p, y, u, f, H);
@@ -1048,6 +1049,7 @@ __global__ void __launch_bounds__(TcShape<MK, NS, HID>::THREADS, 1) phnn_tc_kern
         c.split = split;
         c.store = (c.qt == 0);
         c.tape = tape;
+        c.scratch = p.scratch ? p.scratch + (size_t)blockIdx.x * tc_scratch_floats_per_cta(NS, p.T, p.S) : nullptr;
         c.sck = nullptr;
         c.ev = 0;
         mbar_wait(&bars[SH::B_SMALL], 0);
