@@ -13,7 +13,7 @@
  *     phnn_last_error() returns a thread-local message for the last non-zero return.
  *   - all data pointers are DEVICE pointers to float32, row-major, on the pack's device.
  *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); the library keeps
- *     no global mutable state; a pack is immutable after creation and may be shared.
+ *     no global mutable state; a pack changes only through phnn_pack_set_option and may be shared.
  *   - instances (rows of the leading B dimension) are independent.
  */
 #ifndef PHNN_MPC_H
@@ -77,9 +77,10 @@ int phnn_pack_destroy(phnn_pack *pack);
 int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
 
 /* Kernel selection knobs (no reference counterpart).
- *   "tensor_mode"      0: FP32-FMA kernel only; 2 (default where built): tcgen05 tensor cores, TF32 product + one
- *                      BF16 correction product (FP32-level accuracy); 3: 3xTF32 error compensation (FP32-level
- *                      accuracy, 1.5x the tensor work); 1: plain TF32 (looser).
+ *   "tensor_mode"      0: FP32-FMA kernel only; 4 (default where built): second-generation tcgen05 kernel, three FP16
+ *                      hi/lo products with operand A in tensor memory (FP32-level accuracy); 2: first-generation
+ *                      kernel, TF32 product + one BF16 correction product (FP32-level accuracy); 3: 3xTF32 error
+ *                      compensation (FP32-level accuracy, 1.5x the tensor work of 2); 1: plain TF32 (looser).
  *   "tensor_min_batch" smallest B routed to the tcgen05 kernel (default 1: it beats the FP32-FMA kernel
  *                      at every batch size; small batches go to the latency kernel first).
  *   "latency_max_batch" largest B routed to the latency kernel (one thread per hidden unit, up to 8 instances
@@ -129,6 +130,31 @@ int phnn_mpc_solve(const phnn_pack *pack, const phnn_cost_desc *cost_desc, const
                    float *cost_hist, float *best_cost, long B, int T, double dt, int integrator, double lr,
                    double beta1, double beta2, double eps, int iters, int return_mode, void *workspace,
                    size_t workspace_bytes, void *stream);
+
+/* ---- multi-GPU: fused result exchange -----------------------------------------
+ * Instances are sharded across ranks with no data-path collective; the only exchange is the final
+ * gather of U* / best cost.  Instead of a separate NCCL all_gather the solve kernel itself stores every finished
+ * 128-instance tile into the result buffers of ALL ranks (peer memory over NVLink), overlapped with the tiles still
+ * being solved.  Result buffers are allocated by phnn_peer_alloc (cudaMalloc + CUDA IPC handle), the 64-byte handles
+ * are exchanged by the host code (torch.distributed), and every rank opens the others' with phnn_peer_open.        */
+#define PHNN_MAX_PEERS 8
+typedef struct phnn_peer_desc {
+    int n;                        /* ranks (1..PHNN_MAX_PEERS), own buffer included                        */
+    long long offset;             /* global index of this rank's first instance                            */
+    float *U[PHNN_MAX_PEERS];     /* DEVICE pointers (local or peer-mapped): [B_total, T, m] on every rank  */
+    float *cost[PHNN_MAX_PEERS];  /* [B_total] best cost on every rank, or NULL                            */
+} phnn_peer_desc;
+int phnn_peer_alloc(size_t bytes, int device, void **dptr, void *handle64);
+int phnn_peer_open(const void *handle64, int device, void **dptr);
+int phnn_peer_close(void *dptr, int device);
+int phnn_peer_free(void *dptr, int device);
+/* phnn_mpc_solve + the fused exchange (peers == NULL: identical to phnn_mpc_solve).  Only batches routed to the
+ * tcgen05 kernels support it (PHNN_E_UNSUPPORTED otherwise).  The caller separates consecutive solves that target
+ * the same result buffers with a cross-rank barrier (phnn_mpc_b200/peer.py alternates two buffers).               */
+int phnn_mpc_solve_peer(const phnn_pack *pack, const phnn_cost_desc *cost_desc, const float *x0, float *U_inout,
+                        float *cost_hist, float *best_cost, long B, int T, double dt, int integrator, double lr,
+                        double beta1, double beta2, double eps, int iters, int return_mode, void *workspace,
+                        size_t workspace_bytes, const phnn_peer_desc *peers, void *stream);
 
 /* ---- batched closed loop on the device (the callers either side of the solve) -------------------- */
 

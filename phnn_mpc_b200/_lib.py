@@ -37,6 +37,10 @@ class Episode(ctypes.Structure):
                 ("stability_achieved", ctypes.c_void_p), ("steps", ctypes.c_int)]
 
 
+class PeerDesc(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int), ("offset", ctypes.c_longlong), ("U", ctypes.c_void_p * 8), ("cost", ctypes.c_void_p * 8)]
+
+
 _lib = None
 
 
@@ -65,6 +69,15 @@ def lib():
                                  ctypes.c_size_t, vp]
     L.phnn_mpc_solve.argtypes = [vp, ctypes.POINTER(CostDesc), vp, vp, vp, vp, ll, ci, cd, ci, cd, cd, cd, cd, ci, ci,
                                  vp, ctypes.c_size_t, vp]
+    L.phnn_mpc_solve_peer.argtypes = [vp, ctypes.POINTER(CostDesc), vp, vp, vp, vp, ll, ci, cd, ci, cd, cd, cd, cd, ci, ci,
+                                      vp, ctypes.c_size_t, ctypes.POINTER(PeerDesc), vp]
+    L.phnn_mpc_solve_peer.restype = ci
+    L.phnn_peer_alloc.argtypes = [ctypes.c_size_t, ci, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.phnn_peer_open.argtypes = [ctypes.c_char_p, ci, ctypes.POINTER(vp)]
+    L.phnn_peer_close.argtypes = [vp, ci]
+    L.phnn_peer_free.argtypes = [vp, ci]
+    for f in ("phnn_peer_alloc", "phnn_peer_open", "phnn_peer_close", "phnn_peer_free"):
+        getattr(L, f).restype = ci
     L.phnn_pack_set_option.argtypes = [vp, ctypes.c_char_p, ll]
     L.phnn_pack_set_option.restype = ci
     L.phnn_pack_get_option.argtypes = [vp, ctypes.c_char_p]
@@ -89,7 +102,8 @@ def lib():
 
 EXPORTS = ["phnn_last_error", "phnn_version", "phnn_pack_create", "phnn_pack_destroy", "phnn_pack_dims",
            "phnn_forward", "phnn_vjp", "phnn_rollout", "phnn_workspace_bytes", "phnn_cost_grad", "phnn_mpc_solve", "phnn_ffma_probe", "phnn_tf32_probe",
-           "phnn_pack_set_option", "phnn_pack_get_option", "phnn_plant_step", "phnn_state_to_f32", "phnn_shift_controls"]
+           "phnn_pack_set_option", "phnn_pack_get_option", "phnn_plant_step", "phnn_state_to_f32", "phnn_shift_controls",
+           "phnn_mpc_solve_peer", "phnn_peer_alloc", "phnn_peer_open", "phnn_peer_close", "phnn_peer_free"]
 
 
 def check(rc, what):

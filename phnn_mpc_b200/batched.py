@@ -77,6 +77,25 @@ def rollout(model, x0, U, dt, integrator="rk4", energy_mode=0):
     return (traj, en) if energy_mode else traj
 
 
+def _solve_peer_call(pk, x0, U0, dt, integ, cost_args, lr, b1, b2, eps, iters, rmode, want_hist, peer):
+    """phnn_mpc_solve_peer through ctypes (the torch.library op has no argument for the peer table)"""
+    import ctypes
+    from . import _lib
+    B, T = x0.shape[0], U0.shape[1]
+    cd = ops._Cost(*cost_args)
+    U = U0.clone()
+    hist = torch.empty((iters, B) if want_hist else (0,), dtype=torch.float32, device=x0.device)
+    best = torch.empty((B,), dtype=torch.float32, device=x0.device)
+    ws, nbytes = ops._workspace(pk.handle, B, T, integ, x0.device)
+    d = peer.desc()
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.lib().phnn_mpc_solve_peer(ctypes.c_void_p(pk.handle), ctypes.byref(cd.desc), ops._p(x0), ops._p(U),
+                                                  ops._p(hist) if want_hist else None, ops._p(best), B, T, float(dt), integ,
+                                                  float(lr), float(b1), float(b2), float(eps), int(iters), int(rmode),
+                                                  ops._p(ws), nbytes, ctypes.byref(d), ops._stream(x0)), "phnn_mpc_solve_peer")
+    return U, hist, best
+
+
 class BatchedMPC:
     """B-instance gradient MPC: iters x {clamp, rollout, cost, adjoint, Adam} in one launch."""
 
@@ -104,9 +123,10 @@ class BatchedMPC:
                                       bool(want_grad), bool(want_traj))
         return cost, (g if want_grad else None), (traj if want_traj else None)
 
-    def solve(self, x0, U0=None, want_hist=False):
+    def solve(self, x0, U0=None, want_hist=False, peer=None):
         """x0 [B,n]; U0 [B,H,m] or None (zeros, the controllers' cold start).
-        Returns dict(U [B,H,m], u0 [B,m], best_cost [B], cost_hist [iters,B]|None) on the device."""
+        Returns dict(U [B,H,m], u0 [B,m], best_cost [B], cost_hist [iters,B]|None) on the device.
+        peer: a peer.PeerGather -- the kernel also stores the results into every rank's result buffers (multi-GPU)."""
         pk = self.pack
         x0 = _dev(x0, pk.device).reshape(-1, pk.n)
         B = x0.shape[0]
@@ -114,7 +134,15 @@ class BatchedMPC:
             U0 = torch.zeros((B, self.horizon, pk.m), dtype=torch.float32, device=pk.device)
         else:
             U0 = _dev(U0, pk.device).reshape(B, self.horizon, pk.m)
+        if peer is not None:
+            return self._solve_peer(pk, x0, U0, want_hist, peer)
         U, hist, best = ops.mpc_solve(pk.handle, x0, U0, self.dt, self.integrator_id, *self.cost.op_args(), self.lr,
                                       self.betas[0], self.betas[1], self.eps, self.iters,
                                       0 if self.return_mode == "last" else 1, bool(want_hist))
+        return {"U": U, "u0": U[:, 0], "best_cost": best, "cost_hist": hist if want_hist else None}
+
+    def _solve_peer(self, pk, x0, U0, want_hist, peer):
+        U, hist, best = _solve_peer_call(pk, ops._chk(x0, "x0"), ops._chk(U0, "U0"), self.dt, self.integrator_id,
+                                         self.cost.op_args(), self.lr, self.betas[0], self.betas[1], self.eps, self.iters,
+                                         0 if self.return_mode == "last" else 1, bool(want_hist), peer)
         return {"U": U, "u0": U[:, 0], "best_cost": best, "cost_hist": hist if want_hist else None}

@@ -268,7 +268,7 @@ static void fill_tc16_small(const phnn_model_desc* d, const Tc16Scales& sc, std:
     const bool has_r = d->kind == PHNN_KIND_PHNN;
     s.assign((size_t)(has_r ? 12 : 5) * np * 4, 0.f);
     auto at = [&](int f, int P, int half, int o) -> float& { return s[((size_t)f * np + P) * 4 + half * 2 + o]; };
-    const float SD = pow2f(sc.eD), SE = pow2f(sc.eE);
+    const float SD = pow2f(sc.eD), SE = pow2f(sc.eE - sc.eB);  // e2 is formed from the dz2 accumulator, which carries S_B
     for (int k = 0; k < h; ++k) {
         const int P = k >> 1, o = k & 1;
         at(0, P, 0, o) = d->W1[k * n + 0]; at(0, P, 1, o) = d->W1[k * n + 1];
@@ -424,6 +424,7 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         pk->base.s16[3] = pow2f(-(sc.eE + sc.eB));
         pk->base.s16[4] = pow2f(sc.eA);
         pk->base.s16[5] = pow2f(-sc.eD);
+        pk->base.s16[6] = pow2f(sc.eE + sc.eB);
         pk->base.wexp16 = sc.wexp;
         // default: the second-generation kernel (three FP16 products, operand A in tensor memory): FP32-level accuracy,
         // measured 1.2-1.3x the first-generation kernel's default (mode 2: TF32 + BF16 correction product)
@@ -766,10 +767,10 @@ extern "C" int phnn_cost_grad(const phnn_pack* pk, const phnn_cost_desc* cd, con
     return launch(pk, P, stream);
 }
 
-extern "C" int phnn_mpc_solve(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, float* U_inout,
-                              float* cost_hist, float* best_cost, long B, int T, double dt, int integrator, double lr,
-                              double beta1, double beta2, double eps, int iters, int return_mode, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+extern "C" int phnn_mpc_solve_peer(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, float* U_inout,
+                                   float* cost_hist, float* best_cost, long B, int T, double dt, int integrator, double lr,
+                                   double beta1, double beta2, double eps, int iters, int return_mode, void* workspace,
+                                   size_t workspace_bytes, const phnn_peer_desc* peers, void* stream) {
     if (pk && B == 0) return 0;
     if (!pk || !x0 || !U_inout || B < 0 || T <= 0 || iters < 0)
         return fail(PHNN_E_ARG, "phnn_mpc_solve: bad argument");
@@ -785,7 +786,76 @@ extern "C" int phnn_mpc_solve(const phnn_pack* pk, const phnn_cost_desc* cd, con
     P.mode = MODE_SOLVE; P.B = B; P.T = T; P.iters = iters; P.return_mode = return_mode; P.want_grad = 1;
     P.lr = lr; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps;
     P.x0 = x0; P.U = U_inout; P.cost_hist = cost_hist; P.cost = best_cost; P.ws = (float*)workspace;
+    P.npeer = 0;
+    if (peers) {
+        if (peers->n < 1 || peers->n > PHNN_MAX_PEERS || peers->offset < 0)
+            return fail(PHNN_E_ARG, "phnn_mpc_solve_peer: 1..%d peers, offset >= 0", PHNN_MAX_PEERS);
+        const bool lat = pk->lat_max_batch > 0 && B <= pk->lat_max_batch && has_lat_shape(pk->mk, pk->n, pk->h);
+        const bool tc = !lat && pk->tc_mode != 0 && pk->d_wtc && B >= pk->tc_min_batch;
+        if (!tc || iters == 0)
+            return fail(PHNN_E_UNSUPPORTED, "phnn_mpc_solve_peer: the fused exchange needs a batch routed to a tcgen05 kernel and iters > 0");
+        P.npeer = peers->n;
+        P.peer_off = peers->offset;
+        for (int r = 0; r < peers->n; ++r) {
+            if (!peers->U[r]) return fail(PHNN_E_ARG, "phnn_mpc_solve_peer: peer %d has no result buffer", r);
+            P.peerU[r] = peers->U[r];
+            P.peerC[r] = best_cost ? peers->cost[r] : nullptr;
+        }
+    }
     return launch(pk, P, stream);
+}
+
+extern "C" int phnn_mpc_solve(const phnn_pack* pk, const phnn_cost_desc* cd, const float* x0, float* U_inout,
+                              float* cost_hist, float* best_cost, long B, int T, double dt, int integrator, double lr,
+                              double beta1, double beta2, double eps, int iters, int return_mode, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    return phnn_mpc_solve_peer(pk, cd, x0, U_inout, cost_hist, best_cost, B, T, dt, integrator, lr, beta1, beta2, eps, iters,
+                               return_mode, workspace, workspace_bytes, nullptr, stream);
+}
+
+// ---- result buffers shared between the ranks of one node (CUDA IPC) -------------------------------------
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+extern "C" int phnn_peer_alloc(size_t bytes, int device, void** dptr, void* handle64) {
+    if (!dptr || !handle64 || bytes == 0) return fail(PHNN_E_ARG, "phnn_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(device);
+    CUDA_TRY(cudaMalloc(dptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dptr);
+        *dptr = nullptr;
+        return cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+extern "C" int phnn_peer_open(const void* handle64, int device, void** dptr) {
+    if (!dptr || !handle64) return fail(PHNN_E_ARG, "phnn_peer_open: bad argument");
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int phnn_peer_close(void* dptr, int device) {
+    if (!dptr) return 0;
+    DeviceGuard g(device);
+    CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+extern "C" int phnn_peer_free(void* dptr, int device) {
+    if (!dptr) return 0;
+    DeviceGuard g(device);
+    CUDA_TRY(cudaFree(dptr));
+    return 0;
 }
 
 // ---- measurement utility: sustained FP32-FMA rate of this GPU (roofline denominator for the

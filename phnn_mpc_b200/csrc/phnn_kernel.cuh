@@ -87,7 +87,7 @@ struct KParams {
     const unsigned char* wtc16;  // pre-swizzled K-blocks of W2 and W2^T, rows of [b_hi (32 fp16) | b_lo (32 fp16)], scaled by S_B
     const float* wsmall16;       // field-major small-layer records (Tc16Shape)
     float s16[8];                // exact power-of-two scales: [0] 1/(S_a S_B), [1] 1/(S_delta S_B), [2] 1/S_B, [3] 1/(S_e S_B),
-                                 // [4] S_a, [5] 1/S_delta
+                                 // [4] S_a, [5] 1/S_delta, [6] S_e S_B
     int wexp16;                  // per-instance adjoint scale: max |w'| lands in [2^wexp16, 2^(wexp16+1))
     // model constants
     float Jm[16];  // MK 0/1: J - J^T ; MK 2: the canonical J buffer
@@ -125,6 +125,12 @@ struct KParams {
     float* scratch;    // tcgen05 kernels: per-CTA stage states [T*S][n][128] + R_net sums / grad H [T*S][16][128] of the
                        // (tile, iteration) unit in flight; nullptr: the stage states live in the tile's workspace
     long long* dbg;    // optional profiling output (PHNN_TC_PROFILE builds)
+    // fused result exchange (multi-GPU solve): after the last iteration of a tile the CTA stores the tile's controls
+    // and best costs straight into the result buffers of every rank (peer memory over NVLink)
+    int npeer;             // 0: no exchange
+    long long peer_off;    // global index of this rank's first instance
+    float* peerU[8];       // [B_total, T] on every rank (own buffer included)
+    float* peerC[8];       // [B_total] best cost, nullable
 };
 
 // floats of workspace per tile of TW instances: stage states [T*S][NS][TW], Adam m, v and best
@@ -308,6 +314,7 @@ struct Ctx {
     __device__ __forceinline__ float* row_own(float* buf, int k) const { return buf + k * GI + (chunk << 3); }
     __device__ __forceinline__ void begin_unit(const KParams&, long long) {}
     __device__ __forceinline__ float* unit_scratch() const { return nullptr; }
+    __device__ __forceinline__ void peer_store(const KParams&, long long) {}
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
         phnn::eval_fwd(*this, p, y, u, f, H);
     }
@@ -1203,6 +1210,7 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
         if (p.cost) p.cost[b] = best;
     }
     sched.done(c, unit);
+    if (solve && it == p.iters && p.npeer > 0) c.peer_store(p, tile);
   }
   // a solve with zero iterations still clamps / copies the initial guess (src/mpc_controller.py:203-207)
   if (p.mode == MODE_SOLVE && p.iters == 0) {

@@ -90,6 +90,7 @@ struct LatCtx {
     __device__ __forceinline__ void gbar() const { group_bar(1 + inst, SH::HID); }  // the threads of my instance
     __device__ __forceinline__ void begin_unit(const KParams&, long long) {}
     __device__ __forceinline__ float* unit_scratch() const { return nullptr; }
+    __device__ __forceinline__ void peer_store(const KParams&, long long) {}
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
         lat_eval_fwd(*this, p, y, u, f, H);
     }

@@ -118,6 +118,22 @@ __device__ __forceinline__ float2 frag2(const uint32_t (&r)[16], int k, int rsel
     return make_float2(__uint_as_float(r[4 * k + 2 * rsel]), __uint_as_float(r[4 * k + 2 * rsel + 1]));
 }
 
+// tanh of a pair for this kernel.  PHNN_TC16_TANH_BRANCH = 1 keeps the x - x^3/3 branch of tanh_tc2 below |x| = 0.04;
+// 0 evaluates 1 - 2 / (exp(2x) + 1) everywhere: absolute error ~1.5e-7 (the FP32 rounding of a value near 1), which is
+// what the products that consume the activations see anyway; half the instructions (7 instead of 14 per pair).
+#ifndef PHNN_TC16_TANH_BRANCH
+#define PHNN_TC16_TANH_BRANCH 0
+#endif
+__device__ __forceinline__ float2 tanh16(float2 x) {
+#if PHNN_TC16_TANH_BRANCH
+    return tanh_tc2(x);
+#else
+    const float2 t = mul2(x, bc2(2.8853900817779268f));
+    const float2 d = add2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), bc2(1.0f));
+    return fma2(bc2(-2.0f), make_float2(rcp_approx(d.x), rcp_approx(d.y)), bc2(1.0f));
+#endif
+}
+
 template <class SH> struct Tc16Ctx;
 template <class SH>
 __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
@@ -168,12 +184,14 @@ struct Tc16Ctx {
     // idle one for the first product of an evaluation, the one being consumed (in place) for the second
     __device__ __forceinline__ uint32_t feed_col() const { return ((qfeed & 1u) ^ 1u) * SH::HID; }
     // operand A of K-block kb: v[rsel][k] = the pair of units (32 kb + 8 k + 2 cq, +1) of instance rsel, times `scale`
+    template <bool SCALED>
     __device__ __forceinline__ void put_block(int kb, const float2 (&v)[2][4], float scale) {
         uint32_t q[16];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int rsel = 0; rsel < 2; ++rsel) split_f16x2(mul2(v[rsel][k], bc2(scale)), q[2 * k + rsel], q[2 * (4 + k) + rsel]);
+            for (int rsel = 0; rsel < 2; ++rsel)
+                split_f16x2(SCALED ? mul2(v[rsel][k], bc2(scale)) : v[rsel][k], q[2 * k + rsel], q[2 * (4 + k) + rsel]);
         tmem_st_pairs(tl16 + feed_col() + kb * 32, q);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
@@ -192,6 +210,7 @@ struct Tc16Ctx {
     }
     float* scratch;  // per-CTA stage states + R_net sums / grad H of the unit in flight (nullptr: no adjoint follows)
     __device__ __forceinline__ float* unit_scratch() const { return scratch; }
+    __device__ __forceinline__ void peer_store(const KParams& p, long long tile) const { tc_peer_store_tile(p, tile, tid); }
     __device__ __forceinline__ void begin_unit(const KParams& p, long long) {
         sck = scratch ? scratch + (size_t)p.T * p.S * NS * TW : nullptr;
     }
@@ -224,8 +243,8 @@ __device__ __forceinline__ void tc16_rfwd(const Tc16Ctx<SH>& c, int kb, const fl
         const int P = tc16_pair(c, kb, k);
         const float4 u01 = F[5 * SH::NP + P], u23 = F[6 * SH::NP + P];
         const float2 br1 = zw(F[2 * SH::NP + P]);
-        const float2 rA = tanh_tc2(pair_affine(u01, u23, yA, br1));
-        const float2 rB = tanh_tc2(pair_affine(u01, u23, yB, br1));
+        const float2 rA = tanh16(pair_affine(u01, u23, yA, br1));
+        const float2 rB = tanh16(pair_affine(u01, u23, yB, br1));
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
             const float4 cc = F[(7 + j) * SH::NP + P];
@@ -274,15 +293,15 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                 const int P = tc16_pair(c, kb, k);
                 const float4 w01 = F[P], w23 = F[NP + P];
                 const float2 b1 = xy(F[2 * NP + P]);
-                a[0][k] = tanh_tc2(pair_affine(w01, w23, zA, b1));
-                a[1][k] = tanh_tc2(pair_affine(w01, w23, zB, b1));
+                a[0][k] = tanh16(pair_affine(w01, w23, zA, b1));
+                a[1][k] = tanh16(pair_affine(w01, w23, zB, b1));
                 if (k & 1) sched_fence();
             }
             if (c.tape) {
 #pragma unroll
                 for (int s = 0; s < 4; ++s) *c.tape4(1, kb, s) = pack4(a[s >> 1][2 * (s & 1)], a[s >> 1][2 * (s & 1) + 1]);  // read back in phase C
             }
-            c.put_block(kb, a, p.s16[4]);
+            c.template put_block<true>(kb, a, p.s16[4]);
             if constexpr (SH::HAS_R) {
                 if (kb >= PHNN_TC_RSKEW) tc16_rfwd<0, 2>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
             }
@@ -306,7 +325,7 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                 const float4 m = F[3 * NP + tc16_pair(c, kb, k)];  // {b2 pair, w3 * S_delta pair}
 #pragma unroll
                 for (int rsel = 0; rsel < 2; ++rsel) {
-                    const float2 t = tanh_tc2(fma2(frag2(zr, k, rsel), bc2(isz), xy(m)));
+                    const float2 t = tanh16(fma2(frag2(zr, k, rsel), bc2(isz), xy(m)));
                     if (rsel) HpB = fma2(zw(m), t, HpB); else HpA = fma2(zw(m), t, HpA);
                     d[rsel][k] = mul2(one_minus_sq(t), zw(m));
                     a2[rsel][k] = t;
@@ -317,7 +336,7 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
 #pragma unroll
                 for (int s = 0; s < 4; ++s) __stcs(c.tape4(0, kb, s), pack4(a2[s >> 1][2 * (s & 1)], a2[s >> 1][2 * (s & 1) + 1]));
             }
-            c.put_block(kb, d, 1.0f);
+            c.template put_block<false>(kb, d, 1.0f);
             if constexpr (SH::HAS_R) {
                 if (kb >= PHNN_TC_RSKEW) tc16_rfwd<2, 4>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
             }
@@ -353,7 +372,7 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                     const float4 w01 = F[P], w23 = F[NP + P];
 #pragma unroll
                     for (int rsel = 0; rsel < 2; ++rsel) {
-                        g[rsel][k] = mul2(frag2(gr, k, rsel), bc2(isg));
+                        g[rsel][k] = frag2(gr, k, rsel);  // g1 * S_delta S_B: the exact power of two is applied to the totals
                         const float2 t = mul2(one_minus_sq(tape_pair(ac, rsel, k)), g[rsel][k]);
                         if (rsel) pair_scatter(w01, w23, t, GB); else pair_scatter(w01, w23, t, GA);
                     }
@@ -369,16 +388,16 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                     const int P = tc16_pair(c, kb, k);
                     const float4 w01 = F[P], w23 = F[NP + P];
                     const float2 b1 = xy(F[2 * NP + P]);
-                    const float2 aA = tanh_tc2(pair_affine(w01, w23, zA, b1));
-                    const float2 aB = tanh_tc2(pair_affine(w01, w23, zB, b1));
-                    pair_scatter(w01, w23, mul2(one_minus_sq(aA), mul2(frag2(gr, k, 0), bc2(isg))), GA);
-                    pair_scatter(w01, w23, mul2(one_minus_sq(aB), mul2(frag2(gr, k, 1), bc2(isg))), GB);
+                    const float2 aA = tanh16(pair_affine(w01, w23, zA, b1));
+                    const float2 aB = tanh16(pair_affine(w01, w23, zB, b1));
+                    pair_scatter(w01, w23, mul2(one_minus_sq(aA), frag2(gr, k, 0)), GA);
+                    pair_scatter(w01, w23, mul2(one_minus_sq(aB), frag2(gr, k, 1)), GB);
                     if (k & 1) sched_fence();
                 }
             });
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dH[i] = c.quad_own_sum(GA[i].x + GA[i].y, GB[i].x + GB[i].y);
+        for (int i = 0; i < 4; ++i) dH[i] = c.quad_own_sum(GA[i].x + GA[i].y, GB[i].x + GB[i].y) * isg;
         tc_fence_before();
     }
     float Sp[12];
@@ -445,8 +464,8 @@ __device__ __forceinline__ void tc16_rback(const Tc16Ctx<SH>& c, int kb, const f
         }
         const float4 u01 = F[5 * SH::NP + P], u23 = F[6 * SH::NP + P];
         const float2 br1 = zw(F[2 * SH::NP + P]);
-        const float2 rA = tanh_tc2(pair_affine(u01, u23, yA, br1));
-        const float2 rB = tanh_tc2(pair_affine(u01, u23, yB, br1));
+        const float2 rA = tanh16(pair_affine(u01, u23, yA, br1));
+        const float2 rB = tanh16(pair_affine(u01, u23, yB, br1));
         pair_scatter(u01, u23, mul2(rbA, one_minus_sq(rA)), XA);
         pair_scatter(u01, u23, mul2(rbB, one_minus_sq(rB)), XB);
         sched_fence();
@@ -531,8 +550,11 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
         isc = __uint_as_float((uint32_t)(254 - se) << 23);
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] *= sc;
+        // the R_net chain accumulates into the same sums as the dg1 half of xbar_H, which is kept in accumulator units
+        // (dg1 * S_e S_B): bring Rb there too, so one exact scale serves the whole sum
+        const float scr = sc * p.s16[6];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) Rb[i] *= sc;
+        for (int i = 0; i < 10; ++i) Rb[i] *= scr;
     }
     float wA[4], wB[4], yA[4], yB[4], RbA[10], RbB[10];
 #pragma unroll
@@ -576,7 +598,7 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
                     pair_scatter(w01, w23, mul2(mul2(a1, da[1][k]), tape_pair(gc, 1, k)), TB);
                 }
             }
-            c.put_block(kb, da, 1.0f);
+            c.template put_block<false>(kb, da, 1.0f);
             if constexpr (SH::HAS_R) {
                 if (kb >= PHNN_TC_RSKEW) tc16_rback<0, 2>(c, kb - PHNN_TC_RSKEW, yA, yB, RbA, RbB, XA, XB);
             }
@@ -592,7 +614,6 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
         float4 a2n[4];
         c.template tape_load<true>(0, 0, a2n);
         const uint32_t tacc = c.acc_wait();
-        const float isb = p.s16[2];
         for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dz)[16]) {
             float4 a2q[4];
 #pragma unroll
@@ -601,15 +622,14 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
             float2 e2[2][4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float2 m2w3 = xy(F[4 * NP + tc16_pair(c, kb, k)]);  // -2 w3 * S_e pair
+                const float2 m2w3 = xy(F[4 * NP + tc16_pair(c, kb, k)]);  // -2 w3 * S_e / S_B pair (dz2 arrives times S_B)
 #pragma unroll
                 for (int rsel = 0; rsel < 2; ++rsel) {
                     const float2 a2 = tape_pair(a2q, rsel, k);
-                    const float2 dzz = mul2(frag2(dz, k, rsel), bc2(isb));
-                    e2[rsel][k] = mul2(mul2(a2, mul2(one_minus_sq(a2), dzz)), m2w3);
+                    e2[rsel][k] = mul2(mul2(a2, mul2(one_minus_sq(a2), frag2(dz, k, rsel))), m2w3);
                 }
             }
-            c.put_block(kb, e2, 1.0f);
+            c.template put_block<false>(kb, e2, 1.0f);
             if constexpr (SH::HAS_R) {
                 if (kb >= PHNN_TC_RSKEW) tc16_rback<2, 4>(c, kb - PHNN_TC_RSKEW, yA, yB, RbA, RbB, XA, XB);
             }
@@ -625,7 +645,6 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
         float4 a1n[4];
         c.template tape_load<true>(1, 0, a1n);
         const uint32_t tacc = c.acc_wait();
-        const float isd = p.s16[3];
         for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dg)[16]) {
             float4 ac[4];
 #pragma unroll
@@ -635,16 +654,20 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
             for (int k = 0; k < 4; ++k) {
                 const int P = tc16_pair(c, kb, k);
                 const float4 w01 = F[P], w23 = F[NP + P];
-                pair_scatter(w01, w23, mul2(one_minus_sq(tape_pair(ac, 0, k)), mul2(frag2(dg, k, 0), bc2(isd))), XA);
-                pair_scatter(w01, w23, mul2(one_minus_sq(tape_pair(ac, 1, k)), mul2(frag2(dg, k, 1), bc2(isd))), XB);
+                pair_scatter(w01, w23, mul2(one_minus_sq(tape_pair(ac, 0, k)), frag2(dg, k, 0)), XA);
+                pair_scatter(w01, w23, mul2(one_minus_sq(tape_pair(ac, 1, k)), frag2(dg, k, 1)), XB);
             }
         });
         tc_fence_before();
     }
+    // T is in units of the taped g1 (g1 * S_delta S_B), X in units of the dg1 accumulator (* S_e S_B): exact powers of two
     float X4[4];
+    {
+        const float ct = -2.f * p.s16[1], cx = p.s16[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        X4[i] = c.quad_own_sum(fmaf(-2.f, TA[i].x + TA[i].y, XA[i].x + XA[i].y), fmaf(-2.f, TB[i].x + TB[i].y, XB[i].x + XB[i].y)) * isc;
+        for (int i = 0; i < 4; ++i)
+            X4[i] = c.quad_own_sum(fmaf(ct, TA[i].x + TA[i].y, cx * (XA[i].x + XA[i].y)), fmaf(ct, TB[i].x + TB[i].y, cx * (XB[i].x + XB[i].y))) * isc;
+    }
     if constexpr (SH::MK == MK_CANON) {
         // chain through z = [q, M(theta) qdot] and M^-1(theta) (src/mass_matrix.py:310-362), SURVEY.md Appendix A
         float pd[2];
@@ -765,9 +788,9 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID>::THREADS, 1) phnn_tc16_
                     const uint32_t afeed = tbase + (par ^ 1u) * HID;
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
-                        mbar_wait_sleep(&bars[SH::B_AFULL + kb], par, PHNN_TC_MMA_SLEEP);
+                        mbar_wait(&bars[SH::B_AFULL + kb], par);
                         const uint32_t e = bent % SH::NBE;
-                        mbar_wait_sleep(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u, PHNN_TC_MMA_SLEEP);
+                        mbar_wait(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
                         tc_fence_after();
                         const uint32_t b_t = b_base + e * SH::B_TILE;
                         const uint32_t a_hi = afeed + kb * 32, a_lo = a_hi + 16;
@@ -828,7 +851,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID>::THREADS, 1) phnn_tc16_
                             }
                         }
                         const uint32_t e = bent % SH::NBE;
-                        mbar_wait_sleep(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u, PHNN_TC_PROD_SLEEP);
+                        mbar_wait(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u);
                         mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
                         bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)kb * SH::B_TILE, SH::B_TILE, &bars[SH::B_BFULL + e]);
                         ++bent;

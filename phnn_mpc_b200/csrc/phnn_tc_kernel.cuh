@@ -266,6 +266,31 @@ __device__ __forceinline__ float2 tanh_tc2(float2 x) {
 #define PHNN_TC_RFENCE 4
 #endif
 
+
+// Fused result exchange of the multi-GPU solve: the 256 element threads of the CTA copy the finished tile's controls
+// (a contiguous block of 128 T floats) and best costs from this rank's buffers into the result buffers of all ranks --
+// plain coalesced 16-byte stores to peer-mapped addresses, travelling over NVLink while the other CTAs keep computing.
+__device__ __forceinline__ void tc_peer_store_tile(const KParams& p, long long tile, int tid) {
+    group_bar(5, 256);  // every row of the tile has been written by its owner thread
+    const long long b0 = tile * 128;
+    const long long rows = (p.B - b0) < 128 ? (p.B - b0) : 128;
+    const long long nfl = rows * p.T;
+    const float* src = p.U + b0 * p.T;
+    const long long goff = (p.peer_off + b0) * p.T;
+    const bool vec = ((goff & 3) == 0) && ((((size_t)src) & 15) == 0);
+    for (int r = 0; r < p.npeer; ++r) {
+        float* dst = p.peerU[r] + goff;
+        if (vec && ((((size_t)dst) & 15) == 0)) {
+            const long long n4 = nfl >> 2;
+            for (long long i = tid; i < n4; i += 256) reinterpret_cast<float4*>(dst)[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
+            for (long long i = (n4 << 2) + tid; i < nfl; i += 256) dst[i] = __ldcg(src + i);
+        } else {
+            for (long long i = tid; i < nfl; i += 256) dst[i] = __ldcg(src + i);
+        }
+        if (p.peerC[r] && p.cost && tid < rows) p.peerC[r][p.peer_off + b0 + tid] = __ldcg(p.cost + b0 + tid);
+    }
+}
+
 template <class SH> struct TcCtx;
 template <class SH>
 __device__ __forceinline__ void tc_eval_fwd(TcCtx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
@@ -395,6 +420,10 @@ struct TcCtx {
     }
     float* scratch;  // per-CTA stage states + R_net sums / grad H of the unit in flight (nullptr: no adjoint follows)
     __device__ __forceinline__ float* unit_scratch() const { return scratch; }
+    __device__ __forceinline__ void peer_store(const KParams& p, long long tile) const {
+        static_assert(SH::NQ == 2, "peer store assumes 256 element threads");
+        tc_peer_store_tile(p, tile, (int)threadIdx.x);
+    }
     __device__ __forceinline__ void begin_unit(const KParams& p, long long) {
         sck = scratch ? scratch + (size_t)p.T * p.S * NS * TW : nullptr;
     }

@@ -285,13 +285,14 @@ def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
             assert rel_err(best.cpu().numpy(), z[p + "best"]) < hor_tol
 
 
+@pytest.mark.parametrize("mode", [4, 3])
 @pytest.mark.parametrize("B", [1, 127, 129, 700])
 @pytest.mark.parametrize("name", ["cartpole_h256", "canonical"])
-def test_tc_ragged_tiles_vs_oracle(tc_env, B, name):
+def test_tc_ragged_tiles_vs_oracle(tc_env, B, name, mode):
     """partially filled 128-instance tiles, energies in both orderings, against the CPU oracle"""
     from oracle.phnn_oracle import OracleModel
     ops, get_tc = tc_env
-    z, sd, pk = get_tc(name, 3)
+    z, sd, pk = get_tc(name, mode)
     M = OracleModel(sd, KINDS[name])
     rng = np.random.default_rng(B)
     x = (rng.uniform(-1, 1, size=(B, 4)) * [1.0, 0.3, 0.5, 0.5]).astype(np.float32)
@@ -493,12 +494,13 @@ def test_tc_long_horizons_vs_oracle(tc_env, H, mode):
     assert np.abs(U.cpu().numpy() - Uo).max() < 0.05 * 0.015
 
 
-def test_full_size_properties_cfg4(tc_env):
+@pytest.mark.parametrize("mode", [4, 2])
+def test_full_size_properties_cfg4(tc_env, mode):
     """BASELINE cfg4 batch size (65 536 instances, h=256) through size-independent properties: sharding and
     permutation invariance (bit for bit: instances are independent and every reduction order is fixed), bounded
     controls, monotone best cost, zero-iteration solve."""
     ops, get_tc = tc_env
-    z, sd, pk = get_tc("cartpole_h256", 2)
+    z, sd, pk = get_tc("cartpole_h256", mode)
     B, H, iters = 65536, 8, 3
     g = torch.Generator().manual_seed(4)
     x0 = ((torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])).cuda()
