@@ -131,6 +131,28 @@ int phnn_mpc_solve(const phnn_pack *pack, const phnn_cost_desc *cost_desc, const
                    double beta1, double beta2, double eps, int iters, int return_mode, void *workspace,
                    size_t workspace_bytes, void *stream);
 
+/* ---- training: gradients with respect to the WEIGHTS ---------------------------------
+ * The reference trains by unrolling the model over a data sequence and back-propagating a loss of the predicted
+ * trajectory through autograd's double backward (scripts/train_cartpole_phnn.py:108-178,
+ * scripts/train_cartpole_phnn_canonical.py:83-196).  phnn_rollout_vjp is the vector-Jacobian product of
+ * phnn_rollout: given gtraj = dL/dtraj [B,T+1,n] it returns dL/dx0 [B,n], dL/dU [B,T,m] and dL/dtheta for every
+ * parameter, in the reference's state_dict layouts (nn.Linear weight = [out,in]).  One fused launch runs the rollout
+ * and the discrete adjoint and emits, per evaluation, the per-hidden-unit factors of the parameter cotangents
+ * (Wbar2 += delta2 (x) da1 + e2 (x) a1, ...); a second kernel contracts them over (instance, evaluation).
+ * All pointers are DEVICE float32; NULL entries are skipped.  Gradients are OVERWRITTEN, not accumulated.
+ * Built for the latency-kernel shapes (hidden width <= 128: every shipped training config).                     */
+typedef struct phnn_param_grads {
+    float *W1, *b1, *W2, *b2, *W3;       /* H_net.net.{0,2,4}: [h,n] [h] [h,h] [h] [1,h]  (b3 gets no gradient)   */
+    float *Wr1, *br1, *Wr2, *br2;        /* R_net.net.{0,2}:   [h,n] [h] [n*n,h] [n*n]                            */
+    float *Wg1, *bg1, *Wg2, *bg2;        /* G_net.net.{0,2}:   [h,n] [h] [n*m,h] [n*m]                            */
+    float *J;                            /* [n,n] (kind 0; a buffer without gradient in kind 1)                    */
+    float *r_diag;                       /* kind 1: dL/d r_diag [n] (chain through softplus is the caller's)       */
+} phnn_param_grads;
+size_t phnn_rollout_vjp_workspace_bytes(const phnn_pack *pack, long B, int T, int integrator);
+int phnn_rollout_vjp(const phnn_pack *pack, const float *x0, const float *U, const float *gtraj, float *dx0, float *dU,
+                     const phnn_param_grads *grads, long B, int T, double dt, int integrator, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
 /* ---- multi-GPU: fused result exchange -----------------------------------------
  * Instances are sharded across ranks with no data-path collective; the only exchange is the final
  * gather of U* / best cost.  Instead of a separate NCCL all_gather the solve kernel itself stores every finished

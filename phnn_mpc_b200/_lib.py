@@ -37,6 +37,11 @@ class Episode(ctypes.Structure):
                 ("stability_achieved", ctypes.c_void_p), ("steps", ctypes.c_int)]
 
 
+class ParamGrads(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in ("W1", "b1", "W2", "b2", "W3", "Wr1", "br1", "Wr2", "br2", "Wg1", "bg1", "Wg2",
+                                               "bg2", "J", "r_diag")]
+
+
 class PeerDesc(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int), ("offset", ctypes.c_longlong), ("U", ctypes.c_void_p * 8), ("cost", ctypes.c_void_p * 8)]
 
@@ -78,6 +83,10 @@ def lib():
     L.phnn_peer_free.argtypes = [vp, ci]
     for f in ("phnn_peer_alloc", "phnn_peer_open", "phnn_peer_close", "phnn_peer_free"):
         getattr(L, f).restype = ci
+    L.phnn_rollout_vjp_workspace_bytes.argtypes = [vp, ll, ci, ci]
+    L.phnn_rollout_vjp_workspace_bytes.restype = ctypes.c_size_t
+    L.phnn_rollout_vjp.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.POINTER(ParamGrads), ll, ci, cd, ci, vp, ctypes.c_size_t, vp]
+    L.phnn_rollout_vjp.restype = ci
     L.phnn_pack_set_option.argtypes = [vp, ctypes.c_char_p, ll]
     L.phnn_pack_set_option.restype = ci
     L.phnn_pack_get_option.argtypes = [vp, ctypes.c_char_p]
@@ -103,7 +112,7 @@ def lib():
 EXPORTS = ["phnn_last_error", "phnn_version", "phnn_pack_create", "phnn_pack_destroy", "phnn_pack_dims",
            "phnn_forward", "phnn_vjp", "phnn_rollout", "phnn_workspace_bytes", "phnn_cost_grad", "phnn_mpc_solve", "phnn_ffma_probe", "phnn_tf32_probe",
            "phnn_pack_set_option", "phnn_pack_get_option", "phnn_plant_step", "phnn_state_to_f32", "phnn_shift_controls",
-           "phnn_mpc_solve_peer", "phnn_peer_alloc", "phnn_peer_open", "phnn_peer_close", "phnn_peer_free"]
+           "phnn_rollout_vjp", "phnn_rollout_vjp_workspace_bytes", "phnn_mpc_solve_peer", "phnn_peer_alloc", "phnn_peer_open", "phnn_peer_close", "phnn_peer_free"]
 
 
 def check(rc, what):

@@ -813,6 +813,141 @@ extern "C" int phnn_mpc_solve(const phnn_pack* pk, const phnn_cost_desc* cd, con
                                return_mode, workspace, workspace_bytes, nullptr, stream);
 }
 
+// =========================================================================================
+// Training mode: dL/dtheta of a loss of the rolled-out trajectory
+// =========================================================================================
+// C[i][j] (ldc) = alpha * sum_r A[r*lda + i] * B[r*ldb + j]  (B == nullptr: column sums of A, q = 1), i < p, j < q.
+// One CTA per 32 x 32 tile of C and per slice of the rows; slices meet with atomicAdd (C is zeroed first).
+__global__ void __launch_bounds__(256) atb_kernel(const float* __restrict__ A, int lda, int p, const float* __restrict__ B, int ldb, int q,
+                                                  long long rows, float* __restrict__ C, int ldc, float alpha) {
+    __shared__ float sA[32][33], sB[32][33];
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty 0..7
+    const long long per = (rows + gridDim.z - 1) / gridDim.z;
+    const long long r0 = (long long)blockIdx.z * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};  // C[i0 + ty + 8 e][j0 + tx]
+    for (long long rb = r0; rb < r1; rb += 32) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long r = rb + ty + 8 * e;
+            sA[ty + 8 * e][tx] = (r < r1 && i0 + tx < p) ? A[r * lda + i0 + tx] : 0.f;
+            sB[ty + 8 * e][tx] = (r < r1 && j0 + tx < q) ? (B ? B[r * ldb + j0 + tx] : 1.f) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const float b = sB[r][tx];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = fmaf(sA[r][ty + 8 * e], b, acc[e]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = i0 + ty + 8 * e, j = j0 + tx;
+        if (i < p && j < q) atomicAdd(&C[(size_t)i * ldc + j], alpha * acc[e]);
+    }
+}
+
+static int atb(const float* A, int lda, int p, const float* B, int ldb, int q, long long rows, float* C, int ldc, float alpha,
+               cudaStream_t st) {
+    if (!C || rows <= 0) return 0;
+    long long slices = (rows + 2047) / 2048;
+    if (slices > 64) slices = 64;
+    dim3 grid((p + 31) / 32, (q + 31) / 32, (unsigned)slices);
+    atb_kernel<<<grid, 256, 0, st>>>(A, lda, p, B, ldb, q, rows, C, ldc, alpha);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+struct VjpWorkspace {
+    size_t state_bytes, emit_off, bytes;
+    long long rows;
+};
+static VjpWorkspace vjp_workspace(const phnn_pack* pk, long long B, int T, int S) {
+    VjpWorkspace w;
+    w.rows = B * T * S;
+    w.state_bytes = fp32_workspace_bytes(pk, B, T, S);
+    w.emit_off = w.state_bytes;
+    w.bytes = w.emit_off + ((size_t)EMIT_NARR * w.rows * pk->h + (size_t)w.rows * EMIT_SMALL) * sizeof(float);
+    return w;
+}
+
+extern "C" size_t phnn_rollout_vjp_workspace_bytes(const phnn_pack* pk, long B, int T, int integrator) {
+    if (!pk || B <= 0 || T <= 0) return 0;
+    return vjp_workspace(pk, B, T, integrator == PHNN_RK4 ? 4 : 1).bytes;
+}
+
+extern "C" int phnn_rollout_vjp(const phnn_pack* pk, const float* x0, const float* U, const float* gtraj, float* dx0, float* dU,
+                                const phnn_param_grads* gr, long B, int T, double dt, int integrator, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    if (pk && B == 0) return 0;
+    if (!pk || !x0 || !U || !gtraj || B < 0 || T <= 0) return fail(PHNN_E_ARG, "phnn_rollout_vjp: bad argument");
+    if (!has_lat_shape(pk->mk, pk->n, pk->h))
+        return fail(PHNN_E_UNSUPPORTED, "phnn_rollout_vjp: the training mode is built for the latency-kernel shapes (hidden width <= 128)");
+    KParams P = pk->base;
+    int rc = set_integrator(P, integrator, dt);
+    if (rc) return rc;
+    const VjpWorkspace w = vjp_workspace(pk, B, T, P.S);
+    if (!workspace || workspace_bytes < w.bytes)
+        return fail(PHNN_E_WORKSPACE, "phnn_rollout_vjp: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    if (prev != pk->device) CUDA_TRY(cudaSetDevice(pk->device));
+    P.mode = MODE_PARAMGRAD; P.B = B; P.T = T; P.iters = 1; P.want_grad = 1;
+    P.has_ub = 0; P.has_xmin = 0; P.has_xmax = 0; P.Rw = 0.f;
+    P.x0 = x0; P.uin = U; P.gtraj = gtraj; P.out0 = dx0; P.dJdU = dU; P.ws = (float*)workspace;
+    P.emit = gr ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + w.emit_off) : nullptr;
+    P.emit_rows = w.rows;
+    rc = fail(PHNN_E_UNSUPPORTED, "no latency-kernel instantiation");
+#define X(MK, NS, HID) \
+    if (pk->mk == MK && pk->n == NS && pk->h == HID) rc = launch_lat_shape<LatShape<MK, NS, HID>>(pk, P, st);
+    PHNN_LAT_SHAPES(X)
+#undef X
+    if (rc == 0 && gr) {
+        const int h = pk->h, n = pk->n;
+        const long long R = w.rows;
+        const float* E = P.emit;
+        auto arr = [&](int a) { return E + (size_t)a * R * h; };
+        const float* sm = E + (size_t)EMIT_NARR * R * h;
+        struct Out { float* p; size_t n; } outs[] = {{gr->W1, (size_t)h * n}, {gr->b1, (size_t)h}, {gr->W2, (size_t)h * h}, {gr->b2, (size_t)h},
+            {gr->W3, (size_t)h}, {gr->Wr1, (size_t)h * n}, {gr->br1, (size_t)h}, {gr->Wr2, (size_t)n * n * h}, {gr->br2, (size_t)n * n},
+            {gr->Wg1, (size_t)h * n}, {gr->bg1, (size_t)h}, {gr->Wg2, (size_t)n * h}, {gr->bg2, (size_t)n}, {gr->J, (size_t)n * n},
+            {gr->r_diag, (size_t)n}};
+        for (auto& o : outs)
+            if (o.p && rc == 0) rc = (int)cudaMemsetAsync(o.p, 0, o.n * sizeof(float), st);
+        const int SW = EMIT_SMALL;
+        // H_net
+        if (!rc) rc = atb(arr(4), h, h, sm + 4, SW, n, R, gr->W1, n, 1.f, st);   // delta1 (x) w
+        if (!rc) rc = atb(arr(5), h, h, sm + 0, SW, n, R, gr->W1, n, 1.f, st);   // zbar1 (x) z
+        if (!rc) rc = atb(arr(5), h, h, nullptr, 0, 1, R, gr->b1, 1, 1.f, st);
+        if (!rc) rc = atb(arr(2), h, h, arr(1), h, h, R, gr->W2, h, 1.f, st);    // delta2 (x) da1
+        if (!rc) rc = atb(arr(3), h, h, arr(0), h, h, R, gr->W2, h, 1.f, st);    // e2 (x) a1
+        if (!rc) rc = atb(arr(3), h, h, nullptr, 0, 1, R, gr->b2, 1, 1.f, st);
+        if (!rc) rc = atb(arr(6), h, h, nullptr, 0, 1, R, gr->W3, 1, 1.f, st);
+        if (pk->mk != MK_CANON) {
+            if (!rc) rc = atb(arr(8), h, h, sm + 16, SW, n, R, gr->Wr1, n, 1.f, st);         // dr (x) y
+            if (!rc) rc = atb(arr(8), h, h, nullptr, 0, 1, R, gr->br1, 1, 1.f, st);
+            if (!rc) rc = atb(sm + 20, SW, n * n, arr(7), h, h, R, gr->Wr2, h, 1.f, st);     // Rbar_raw (x) r1
+            if (!rc) rc = atb(sm + 20, SW, n * n, nullptr, 0, 1, R, gr->br2, 1, 1.f, st);
+            if (!rc) rc = atb(sm + 8, SW, n, sm + 12, SW, n, R, gr->J, n, 1.f, st);          // J enters as J - J^T: v g^T - g v^T
+            if (!rc) rc = atb(sm + 12, SW, n, sm + 8, SW, n, R, gr->J, n, -1.f, st);
+        } else {
+            if (!rc && gr->r_diag) rc = atb(sm + 36, SW, 2, nullptr, 0, 1, R, gr->r_diag + 2, 1, -1.f, st);  // rows 2,3 of diag r
+        }
+        if (pk->mk == MK_PHNN_GNET) {
+            if (!rc) rc = atb(arr(10), h, h, sm + 16, SW, n, R, gr->Wg1, n, 1.f, st);
+            if (!rc) rc = atb(arr(10), h, h, nullptr, 0, 1, R, gr->bg1, 1, 1.f, st);
+            if (!rc) rc = atb(sm + 40, SW, n, arr(9), h, h, R, gr->Wg2, h, 1.f, st);
+            if (!rc) rc = atb(sm + 40, SW, n, nullptr, 0, 1, R, gr->bg2, 1, 1.f, st);
+        }
+        if (rc > 0) cuda_fail((cudaError_t)rc, "phnn_rollout_vjp reductions");
+    }
+    if (prev != pk->device) cudaSetDevice(prev);
+    return rc;
+}
+
 // ---- result buffers shared between the ranks of one node (CUDA IPC) -------------------------------------
 struct DeviceGuard {
     int prev = -1;

@@ -31,7 +31,13 @@ constexpr int NST = 4;   // ring stages
 constexpr int MAX_CONSUMER_WARPS = 8;
 constexpr int MAX_THREADS = (MAX_CONSUMER_WARPS + 1) * 32;
 
-enum { MODE_FORWARD = 0, MODE_VJP = 1, MODE_ROLLOUT = 2, MODE_COSTGRAD = 3, MODE_SOLVE = 4 };
+enum { MODE_FORWARD = 0, MODE_VJP = 1, MODE_ROLLOUT = 2, MODE_COSTGRAD = 3, MODE_SOLVE = 4, MODE_PARAMGRAD = 5 };
+// MODE_PARAMGRAD (training): rollout, then the discrete adjoint driven by a caller-supplied cotangent
+// of the trajectory (gtraj [B,T+1,n]) instead of the MPC cost; every adjoint evaluation EMITS the per-hidden-unit
+// factors of the parameter cotangents (phnn_lat_kernel.cuh), which phnn_capi.cu contracts over (instance, evaluation)
+// rows into dL/dtheta.  Outputs dL/dx0 in out0 [B,n] and dL/dU in dJdU [B,T].
+constexpr int EMIT_NARR = 11;    // per-row arrays of h floats: a1, da1, delta2, e2, delta1, zbar1, s2*dz2, r1, dr, ag, dg
+constexpr int EMIT_SMALL = 48;   // per-row small record: z@0 w@4 v@8 g@12 y@16 Rbar_raw@20 (16) pdb*g@36 (2) v*u@40 (4)
 enum { MK_PHNN = 0, MK_PHNN_GNET = 1, MK_CANON = 2 };
 
 template <int MK_, int NS_, int HID_>
@@ -131,6 +137,10 @@ struct KParams {
     long long peer_off;    // global index of this rank's first instance
     float* peerU[8];       // [B_total, T] on every rank (own buffer included)
     float* peerC[8];       // [B_total] best cost, nullable
+    // MODE_PARAMGRAD
+    const float* gtraj;    // [B,T+1,n] cotangent of the trajectory
+    float* emit;           // [EMIT_NARR][rows][h] then [rows][EMIT_SMALL], rows = B*T*S
+    long long emit_rows;
 };
 
 // floats of workspace per tile of TW instances: stage states [T*S][NS][TW], Adam m, v and best
@@ -1019,9 +1029,10 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
     float* bestws = ubest ? ubest + (size_t)T * TW : nullptr;
     const bool solve = (p.mode == MODE_SOLVE);
     const bool one_vjp = (p.mode == MODE_VJP);
-    const bool need_adj = solve || one_vjp || (p.mode == MODE_COSTGRAD && p.want_grad);
+    const bool pgrad = (p.mode == MODE_PARAMGRAD);
+    const bool need_adj = solve || one_vjp || pgrad || (p.mode == MODE_COSTGRAD && p.want_grad);
     const float* Uread = solve ? p.U : p.uin;
-    float* traj = (p.mode == MODE_ROLLOUT || p.mode == MODE_COSTGRAD) ? p.out0 : nullptr;
+    float* traj = (p.mode == MODE_ROLLOUT || p.mode == MODE_COSTGRAD) ? p.out0 : nullptr;  // (PARAMGRAD: out0 is dL/dx0)
     // rollout_trajectory's energy list needs one more evaluation, at y_T (src/integrators.py:184)
     const int t_end = one_vjp ? 0 : T + ((p.mode == MODE_ROLLOUT && p.energy_mode == 2) ? 1 : 0);
 
@@ -1131,6 +1142,9 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
         if (one_vjp) {
 #pragma unroll
             for (int i = 0; i < NS; ++i) lam[i] = valid ? p.vin[b * NS + i] : 0.f;
+        } else if (pgrad) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) lam[i] = valid ? p.gtraj[(b * (T + 1) + T) * NS + i] : 0.f;
         } else {
             state_cost<NS>(p, x, lam);
         }
@@ -1183,13 +1197,18 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
             }
             // y now holds x_t (stage 0 state)
             float gl[NS];
-            state_cost<NS>(p, y, gl);
+            if (pgrad) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) gl[i] = valid ? p.gtraj[(b * (T + 1) + t) * NS + i] : 0.f;
+            } else {
+                state_cost<NS>(p, y, gl);
+            }
 #pragma unroll
             for (int i = 0; i < NS; ++i) lam[i] += ysum[i] + gl[i];
-            float g = fmaf(2.f * p.Rw, u, ubsum);
+            float g = pgrad ? ubsum : fmaf(2.f * p.Rw, u, ubsum);
             if (p.has_ub && !(uraw >= p.umin && uraw <= p.umax)) g = 0.f;  // clamp is inside the graph
-            if (p.mode == MODE_COSTGRAD) {
-                if (st) p.dJdU[b * T + t] = g;
+            if (p.mode == MODE_COSTGRAD || pgrad) {
+                if (st && p.dJdU) p.dJdU[b * T + t] = g;
             } else if (st) {
                 if (improved) ubest[t * TW + slot] = u;
                 float m = __ldcg(adam_m + t * TW + slot), vv = __ldcg(adam_v + t * TW + slot);
@@ -1200,6 +1219,10 @@ __device__ __forceinline__ void run_job(ENG& c, const KParams& p, SCHED& sched, 
                 const float den = sqrtf(vv) / bc2s + epsf;
                 p.U[b * T + t] = uraw + (-step_size * m) / den;
             }
+        }
+        if (pgrad && st && p.out0) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) p.out0[b * NS + i] = lam[i];
         }
         best_reg = best;
         if (SCHED::kStateInWorkspace && st) bestws[slot] = best;

@@ -74,7 +74,9 @@ struct LatCtx {
     static constexpr int NS = SH::NS;
     static constexpr int TW = 1;
     __device__ static int ws_extra(const KParams&) { return 0; }
-    __device__ __forceinline__ void set_eval(int) {}
+    __device__ __forceinline__ void set_eval(int e) { ev = e; }
+    int ev;                   // evaluation in flight (t * S + s): row of the training-mode emission
+    long long inst_global;    // index of my instance in the batch
     int k, lane, warp, inst;  // hidden unit, lane, warp within the instance, instance slot of the CTA
     bool store;
     // this hidden unit's rows of the small layers
@@ -339,8 +341,23 @@ __device__ __noinline__ void lat_eval_vjp(LatCtx<SH>& c, const KParams& p, const
     }
     float tot2[2 * NS];
     c.template block_reduce<2 * NS>(red, tot2);
+    // training mode (MODE_PARAMGRAD): the per-unit factors of the parameter cotangents of this evaluation,
+    //   Wbar2 += delta2 (x) da1 + e2 (x) a1,  Wbar1 += delta1 (x) w + zbar1 (x) z,  bbar1 += zbar1,  bbar2 += e2,
+    //   wbar3 += s2 * dz2   (reverse of the double-backward chain of grad H)
+    const size_t erow = p.emit ? (size_t)c.inst_global * ((size_t)p.T * p.S) + c.ev : 0;
+    float* const esmall = p.emit ? p.emit + (size_t)EMIT_NARR * p.emit_rows * SH::HID + erow * EMIT_SMALL : nullptr;
+    auto earr = [&](int a) -> float& { return p.emit[((size_t)a * p.emit_rows + erow) * SH::HID + c.k]; };
+    if (p.emit) {
+        earr(0) = a1; earr(1) = da1; earr(2) = s2 * c.w3; earr(3) = -2.f * a2 * (s2 * dz2) * c.w3;
+        earr(4) = d1; earr(5) = t; earr(6) = s2 * dz2;
+        if (c.store) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { esmall[i] = z[i]; esmall[4 + i] = w[i]; esmall[8 + i] = v[i]; esmall[12 + i] = tot2[i]; esmall[16 + i] = y[i]; }
+        }
+    }
     if constexpr (SH::MK == MK_CANON) {
         const float* g = tot2;
+        if (p.emit && c.store) { esmall[36] = pdb[0] * g[2]; esmall[37] = pdb[1] * g[3]; }
         float zb[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) zb[i] = tot2[NS + i];
@@ -392,6 +409,20 @@ __device__ __noinline__ void lat_eval_vjp(LatCtx<SH>& c, const KParams& p, const
 #pragma unroll
             for (int a = 0; a < NS; ++a) gb = fmaf(c.wg2[a], v[a] * u, gb);
             zg = gb * fmaf(-ag, ag, 1.f);
+        }
+        if (p.emit) {
+            // R_net: Wbar_r2 += Rbar_raw (x) r1, bbar_r2 += Rbar_raw, Wbar_r1 += dr (x) y, bbar_r1 += dr; G_net likewise
+            earr(7) = r1; earr(8) = zb;
+            if constexpr (SH::HAS_GNET) { earr(9) = ag; earr(10) = zg; }
+            if (c.store) {
+#pragma unroll
+                for (int a = 0; a < NS; ++a)
+#pragma unroll
+                    for (int b = 0; b < NS; ++b)
+                        esmall[20 + a * NS + b] = -0.5f * (v[a] * tg[b] + g[a] * sv[b] + v[b] * tg[a] + g[b] * sv[a]);
+#pragma unroll
+                for (int a = 0; a < NS; ++a) esmall[40 + a] = v[a] * u;
+            }
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) red[i] = 0.f;
@@ -465,6 +496,8 @@ __global__ void __launch_bounds__(LatShape<MK, NS, HID>::THREADS, PHNN_LAT_MINBL
     // past the end of the batch leave here (every later barrier is per instance)
     const long long my_instance = (long long)blockIdx.x * p.ng + c.inst;
     if (c.inst >= p.ng || my_instance >= p.B) return;
+    c.inst_global = my_instance;
+    c.ev = 0;
     int n_outer = (p.mode == MODE_SOLVE) ? p.iters : 1;
     StaticSched sched{my_instance, n_outer, 0};
     run_job(c, p, sched, 0);

@@ -2,9 +2,11 @@
 horizon is ONE kernel launch (op phnn_mpc::rollout); the per-step Python loop of the reference
 (src/integrators.py:176-187, 239-248) is gone.  Returned tensors live on the device of ``y0``.
 
-Not carried over: autograd through the rollout (the reference's training scripts use it; the
-MPC path gets dJ/dU from the in-kernel adjoint instead) and ``compare_integrators`` (dead code
-in the reference: it raises under its own torch.no_grad())."""
+``rollout_trajectory_differentiable`` is differentiable where the reference's is: when autograd is recording and the
+model's parameters (or y0 / controls) require a gradient, it returns ``training.trainable_rollout`` -- the backward is
+the fused rollout + adjoint kernel in its training mode (dL/dtheta, dL/dy0, dL/dU), not an autograd tape.  The MPC path
+gets dJ/dU from the in-kernel adjoint.  Not carried over: ``compare_integrators`` (dead code in the reference: it raises
+under its own torch.no_grad())."""
 import torch
 
 from phnn_mpc_b200 import ops
@@ -54,5 +56,10 @@ def rollout_trajectory(model, y0, controls, dt, integrator="rk4"):
 def rollout_trajectory_differentiable(model, y0, controls, dt, integrator="rk4", return_energies=False):
     """trajectory [B,T+1,n]; with return_energies also the reference's energy list
     [H(y0), H(y0), H(y1), ..., H(y_{T-1})]  (src/integrators.py:192-258)"""
+    needs_grad = torch.is_grad_enabled() and (y0.requires_grad or controls.requires_grad or
+                                              any(p.requires_grad for p in model.parameters()))
+    if needs_grad and not return_energies and _pack(model).h <= 128:
+        from phnn_mpc_b200.training import trainable_rollout
+        return trainable_rollout(model, y0, controls, dt, integrator)
     traj, en = _roll(model, y0, controls, dt, integrator, 1 if return_energies else 0)
     return (traj, en) if return_energies else traj

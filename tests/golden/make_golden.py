@@ -371,8 +371,84 @@ def gen_cfg4_shape():
     print("cfg4_shape done; cost[0] first/last =", res["hist"][0, 0], res["hist"][-1, 0])
 
 
+def gen_train():
+    """Weight gradients of the reference's own training losses, by autograd:
+    scripts/train_cartpole_phnn.py:108-178 (pHNN: Euler unroll, position MSE + angle cosine + velocity MSE; the energy
+    anchor term is left out here because it does not involve the rollout) and scripts/train_cartpole_phnn_canonical.py:
+    83-196 (canonical: Euler unroll, position + velocity-reconstruction loss), plus an RK4 trajectory-matching loss
+    through integrators.rollout_trajectory_differentiable.  Batch: 16 windows of 16 steps of data/cartpole_training_data.pt."""
+    from coordinate_transforms import split_state
+    data = torch.load(os.path.join(REF, "data", "cartpole_training_data.pt"))
+    X, Uall = data["states"] if isinstance(data, dict) and "states" in data else None, None
+    if X is None:
+        keys = list(data.keys()) if isinstance(data, dict) else []
+        raise RuntimeError("unexpected training data layout: %s" % keys)
+    Uall = data["controls"] if "controls" in data else data["actions"]
+    g = torch.Generator().manual_seed(11)
+    idx = torch.randint(0, X.shape[0], (16,), generator=g)
+    t0 = torch.randint(0, X.shape[1] - 16, (16,), generator=g)
+    xb = torch.stack([X[i, s:s + 16] for i, s in zip(idx.tolist(), t0.tolist())]).float()     # [16,16,4]
+    ub = torch.stack([Uall[i, s:s + 16] for i, s in zip(idx.tolist(), t0.tolist())]).float()  # [16,16,1]
+    dt = 0.02
+    out = {"x_batch": xb.numpy(), "u_batch": ub.numpy(), "dt": np.float32(dt)}
+
+    def grads_of(model, loss, prefix):
+        model.zero_grad()
+        loss.backward()
+        for k, p_ in model.named_parameters():
+            out[prefix + "/" + k] = (p_.grad if p_.grad is not None else torch.zeros_like(p_)).detach().numpy().copy()
+        out[prefix + "/loss"] = np.float32(loss.item())
+
+    # --- pHNN (scripts/train_cartpole_phnn.py:108-160 without the energy anchor) ---
+    torch.manual_seed(0)
+    model = pHNN(os.path.join(CFG, "cartpole_phnn.yaml"))
+    loss_fn = torch.nn.MSELoss()
+    x0b = xb[:, 0, :].clone().requires_grad_(True)
+    Xp = [x0b]
+    for t in range(xb.shape[1] - 1):
+        dx, _ = model(Xp[-1], ub[:, t, :])
+        Xp.append(Xp[-1] + dt * dx)
+    Xp = torch.stack(Xp, 1)
+    loss = (loss_fn(Xp[:, :, 0], xb[:, :, 0]) + torch.mean(1 - torch.cos(Xp[:, :, 1] - xb[:, :, 1])) +
+            loss_fn(Xp[:, :, 2:], xb[:, :, 2:]))
+    grads_of(model, loss, "phnn_euler")
+    out["phnn_euler/x0_grad"] = x0b.grad.numpy().copy()
+    out["phnn_euler/traj"] = Xp.detach().numpy()
+    for k, v in model.state_dict().items():
+        out["sd_phnn/" + k] = v.detach().numpy().copy()
+    # RK4 trajectory matching through the reference's differentiable rollout
+    Ug = ub[:, :-1, :].clone().requires_grad_(True)
+    tr = rollout_trajectory_differentiable(model, xb[:, 0, :].clone().requires_grad_(True), Ug, dt, "rk4")
+    loss = ((tr - xb) ** 2).mean()
+    grads_of(model, loss, "phnn_rk4")
+    out["phnn_rk4/U_grad"] = Ug.grad.numpy().copy()
+
+    # --- canonical (scripts/train_cartpole_phnn_canonical.py:83-180, integrator='euler') ---
+    torch.manual_seed(0)
+    cm = pHNN_Canonical(os.path.join(CFG, "cartpole_phnn.yaml"))
+    with torch.no_grad():
+        cm.M_net.log_a.copy_(torch.tensor(0.25)); cm.M_net.b.copy_(torch.tensor(0.35)); cm.M_net.log_c.copy_(torch.tensor(-0.4))
+        cm.R_diag_raw.copy_(torch.tensor([0.1, -0.3, 0.5, 1.2]))
+    y0 = xb[:, 0, :].clone().requires_grad_(True)
+    ys, vel = [y0], []
+    for t in range(xb.shape[1] - 1):
+        dy, _, inter = cm(ys[-1], ub[:, t, :], return_intermediate=True)
+        ys.append(ys[-1] + dt * dy)
+        _, qd_true = split_state(xb[:, t, :])
+        vel.append(torch.sum((inter["q_dot_reconstructed"] - qd_true) ** 2, dim=1).mean())
+    yp = torch.stack(ys, 1)
+    l_pos = torch.mean((yp[:, :, 0] - xb[:, :, 0]) ** 2) + torch.mean(1 - torch.cos(yp[:, :, 1] - xb[:, :, 1]))
+    loss = l_pos + torch.mean(torch.stack(vel))
+    grads_of(cm, loss, "canon_euler")
+    out["canon_euler/traj"] = yp.detach().numpy()
+    for k, v in cm.state_dict().items():
+        out["sd_canon/" + k] = v.detach().numpy().copy()
+    np.savez(os.path.join(HERE, "train_grads.npz"), **out)
+    print("train_grads done; losses", out["phnn_euler/loss"], out["phnn_rk4/loss"], out["canon_euler/loss"])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape"]
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "train"]
     if "pendulum" in which:
         gen_pendulum()
     if "h128" in which:
@@ -385,3 +461,5 @@ if __name__ == "__main__":
         gen_closed_loop()
     if "cfg4_shape" in which:
         gen_cfg4_shape()
+    if "train" in which:
+        gen_train()
