@@ -36,7 +36,11 @@ template <int MK_, int NS_, int HID_>
 struct Tc16Shape {
     static_assert((MK_ == MK_PHNN || MK_ == MK_CANON) && NS_ == 4, "tensor-core path: cart-pole pHNN (fixed G) and canonical pHNN, n = 4");
     static constexpr int MK = MK_, NS = NS_, HID = HID_, NN = NS * NS;
+#ifdef PHNN_TC16_EXP_NOR  // timing experiment (wrong results): no R_net work
+    static constexpr bool HAS_R = false;
+#else
     static constexpr bool HAS_R = (MK != MK_CANON);
+#endif
     static constexpr int TM = 128;            // instances per tile (UMMA M)
     static constexpr int NEW = 8;             // element warps: (TMEM lane quadrant, 16-lane half)
     static constexpr int NKB = HID / 32;      // K-blocks of 32 hidden units
@@ -205,6 +209,11 @@ struct Tc16Ctx {
     }
     template <bool LAST>
     __device__ __forceinline__ void tape_load(int which, int kb, float4 (&v)[4]) const {
+#ifdef PHNN_TC16_EXP_NOTAPE  // timing experiment (wrong results): no tape traffic
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v[s] = make_float4(0.1f * which, 0.2f, 0.3f, 0.01f * kb);
+        return;
+#endif
 #pragma unroll
         for (int s = 0; s < 4; ++s) v[s] = LAST ? __ldcs(tape4(which, kb, s)) : __ldcg(tape4(which, kb, s));
     }
@@ -297,10 +306,12 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                 a[1][k] = tanh16(pair_affine(w01, w23, zB, b1));
                 if (k & 1) sched_fence();
             }
+#ifndef PHNN_TC16_EXP_NOTAPE
             if (c.tape) {
 #pragma unroll
                 for (int s = 0; s < 4; ++s) *c.tape4(1, kb, s) = pack4(a[s >> 1][2 * (s & 1)], a[s >> 1][2 * (s & 1) + 1]);  // read back in phase C
             }
+#endif
             c.template put_block<true>(kb, a, p.s16[4]);
             if constexpr (SH::HAS_R) {
                 if (kb >= PHNN_TC_RSKEW) tc16_rfwd<0, 2>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
@@ -332,10 +343,12 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                 }
                 if (k & 1) sched_fence();
             }
+#ifndef PHNN_TC16_EXP_NOTAPE
             if (c.tape) {
 #pragma unroll
                 for (int s = 0; s < 4; ++s) __stcs(c.tape4(0, kb, s), pack4(a2[s >> 1][2 * (s & 1)], a2[s >> 1][2 * (s & 1) + 1]));
             }
+#endif
             c.template put_block<false>(kb, d, 1.0f);
             if constexpr (SH::HAS_R) {
                 if (kb >= PHNN_TC_RSKEW) tc16_rfwd<2, 4>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
@@ -377,8 +390,10 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                         if (rsel) pair_scatter(w01, w23, t, GB); else pair_scatter(w01, w23, t, GA);
                     }
                 }
+#ifndef PHNN_TC16_EXP_NOTAPE
 #pragma unroll
                 for (int s = 0; s < 4; ++s) __stcs(c.tape4(2, kb, s), pack4(g[s >> 1][2 * (s & 1)], g[s >> 1][2 * (s & 1) + 1]));
+#endif
             });
         } else {
             const uint32_t tacc = c.acc_wait();
