@@ -32,6 +32,12 @@
 
 namespace phnn {
 
+// blocks by which the R_net work trails the hand-off of the producing loops: that many blocks of it are left after the
+// last hand-off and cover the tail of the MMA before the wait for its accumulator (measured: 3 beats 2 by 1 %, 1 loses 4 %)
+#ifndef PHNN_TC16_RSKEW
+#define PHNN_TC16_RSKEW 3
+#endif
+
 template <int MK_, int NS_, int HID_>
 struct Tc16Shape {
     static_assert((MK_ == MK_PHNN || MK_ == MK_CANON) && NS_ == 4, "tensor-core path: cart-pole pHNN (fixed G) and canonical pHNN, n = 4");
@@ -42,11 +48,15 @@ struct Tc16Shape {
     static constexpr bool HAS_R = (MK != MK_CANON);
 #endif
     static constexpr int TM = 128;            // instances per tile (UMMA M)
+    static_assert(HID / 32 >= PHNN_TC16_RSKEW, "R_net skew exceeds the number of K-blocks");
     static constexpr int NEW = 8;             // element warps: (TMEM lane quadrant, 16-lane half)
     static constexpr int NKB = HID / 32;      // K-blocks of 32 hidden units
     static constexpr int NP = HID / 2;        // pairs of adjacent hidden units
     static constexpr int B_TILE = HID * 128;  // bytes of the weight tile of one K-block: rows of [b_hi (32 fp16) | b_lo (32 fp16)]
-    static constexpr int NBE = (HID >= 256) ? 5 : 8;  // weight ring entries
+#ifndef PHNN_TC16_NBE
+#define PHNN_TC16_NBE 5
+#endif
+    static constexpr int NBE = (HID >= 256) ? PHNN_TC16_NBE : 8;  // weight ring entries
     static constexpr int TMEM_COLS = (2 * HID <= 32) ? 32 : (2 * HID <= 64) ? 64 : (2 * HID <= 128) ? 128 : (2 * HID <= 256) ? 256 : 512;
     // small weights: field-major arrays of float4, one entry per pair P of adjacent hidden units (2P, 2P+1); every
     // half of a field is the pair {unit 2P, unit 2P+1}
@@ -95,19 +105,23 @@ __device__ __forceinline__ void tmem_st_pairs(uint32_t taddr, const uint32_t (&q
         "r"(q[11]), "r"(q[12]), "r"(q[13]), "r"(q[14]), "r"(q[15])
         : "memory");
 }
+// parity of a K-block as a type: the bodies of the block loops are instantiated for even and odd blocks, so buffers that
+// are filled one block ahead (tape prefetch) ping-pong between two register sets instead of being copied
+template <int P> struct Par { static constexpr int value = P; };
 // visit the NKB 32-column blocks of an accumulator as fragments, the next block's load in flight
 template <int NKB, class F>
 __device__ __forceinline__ void for_acc_frags(uint32_t tacc, F&& body) {
+    static_assert(NKB % 2 == 0, "blocks are visited in pairs");
     uint32_t ra[16], rb[16];
     tmem_ld_frag_issue(tacc, ra);
 #pragma unroll 1
     for (int b = 0; b < NKB; b += 2) {
         tmem_wait(ra);
         tmem_ld_frag_issue(tacc + (b + 1) * 32, rb);
-        body(b, ra);
+        body(b, ra, Par<0>{});
         tmem_wait(rb);
         if (b + 2 < NKB) tmem_ld_frag_issue(tacc + (b + 2) * 32, ra);
-        body(b + 1, rb);
+        body(b + 1, rb, Par<1>{});
     }
 }
 // (already scaled) pair -> fp16x2 hi and fp16x2 lo = fp16(t - hi); element .x sits in the low half (even K index)
@@ -164,6 +178,11 @@ struct Tc16Ctx {
     bool store;
 
     __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(phnn_smem); }
+#ifdef PHNN_TC16_EXP_RLDS  // timing experiment (wrong results): the R_net records of every pair are those of pair 0 (one broadcast address)
+    static constexpr bool kExpRLds = true;
+#else
+    static constexpr bool kExpRLds = false;
+#endif
     __device__ __forceinline__ const float4* fields() const { return reinterpret_cast<const float4*>(phnn_smem + SH::OFF_SMALL); }
     __device__ __forceinline__ void gbar() const { __syncwarp(); }  // the co-owners of an instance are lanes of one quad
     __device__ __forceinline__ float own(float a, float b) const { return (cq & 2) ? b : a; }
@@ -205,6 +224,9 @@ struct Tc16Ctx {
     __device__ __forceinline__ void end_feed() { ++qfeed; }
     // float4 slot of the tape: array which (0 a2, 1 a1, 2 g1), K-block kb, slot = 2 rsel + (k >> 1)
     __device__ __forceinline__ float4* tape4(int which, int kb, int slot) const {
+#ifdef PHNN_TC16_EXP_TAPEL2  // timing experiment (wrong results): every evaluation uses the tape slot of evaluation 0 (L2-resident)
+        return reinterpret_cast<float4*>(tape) + (((size_t)0 * 3 + which) * (SH::NKB * 4) + kb * 4 + slot) * 256 + tid;
+#endif
         return reinterpret_cast<float4*>(tape) + (((size_t)ev * 3 + which) * (SH::NKB * 4) + kb * 4 + slot) * 256 + tid;
     }
     template <bool LAST>
@@ -314,12 +336,12 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
 #endif
             c.template put_block<true>(kb, a, p.s16[4]);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC_RSKEW) tc16_rfwd<0, 2>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
+                if (kb >= PHNN_TC16_RSKEW) tc16_rfwd<0, 2>(c, kb - PHNN_TC16_RSKEW, zA, zB, SpA, SpB);
             }
         }
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rfwd<0, 2>(c, kb, zA, zB, SpA, SpB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rfwd<0, 2>(c, kb, zA, zB, SpA, SpB);
         }
         c.end_feed();
     }
@@ -329,7 +351,7 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
         const uint32_t tacc = c.acc_wait();
         const float isz = p.s16[0];
         float2 HpA = make_float2(0.f, 0.f), HpB = make_float2(0.f, 0.f);
-        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&zr)[16]) {
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&zr)[16], auto) {
             float2 d[2][4], a2[2][4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -351,12 +373,12 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
 #endif
             c.template put_block<false>(kb, d, 1.0f);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC_RSKEW) tc16_rfwd<2, 4>(c, kb - PHNN_TC_RSKEW, zA, zB, SpA, SpB);
+                if (kb >= PHNN_TC16_RSKEW) tc16_rfwd<2, 4>(c, kb - PHNN_TC16_RSKEW, zA, zB, SpA, SpB);
             }
         });
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rfwd<2, 4>(c, kb, zA, zB, SpA, SpB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rfwd<2, 4>(c, kb, zA, zB, SpA, SpB);
         }
         c.end_feed();
         Hown = c.quad_own_sum(HpA.x + HpA.y, HpB.x + HpB.y) * p.s16[5];
@@ -370,13 +392,12 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
         const float isg = p.s16[1];
         if (c.tape) {
             // a1 comes back from the tape (written by this thread in phase A, still in L2)
-            float4 an[4];
-            c.template tape_load<false>(1, 0, an);
+            float4 t0[4], t1[4];
+            c.template tape_load<false>(1, 0, t0);
             const uint32_t tacc = c.acc_wait();
-            for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16]) {
-                float4 ac[4];
-#pragma unroll
-                for (int s = 0; s < 4; ++s) ac[s] = an[s];
+            for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16], auto par) {
+                float4 (&ac)[4] = decltype(par)::value ? t1 : t0;
+                float4 (&an)[4] = decltype(par)::value ? t0 : t1;
                 if (kb + 1 < NKB) c.template tape_load<false>(1, kb + 1, an);
                 float2 g[2][4];
 #pragma unroll
@@ -397,7 +418,7 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
             });
         } else {
             const uint32_t tacc = c.acc_wait();
-            for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16]) {
+            for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16], auto) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int P = tc16_pair(c, kb, k);
@@ -588,14 +609,15 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
     // ---- A3: da1 = s1 * (W1 w) -> operand A of product 1 (dz2 = W2 da1), with the g1 half of xbar_H (sdot1 * g1) and
     //      half of the R_net chain in the same loop ----
     {
-#pragma unroll 1
-        for (int kb = 0; kb < NKB; ++kb) {
-            float4 ac[4], gc[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { ac[s] = an[s]; gc[s] = gn[s]; }
+        float4 an1[4], gn1[4];  // second register set of the tape prefetch (an / gn hold block 0)
+        auto a3_block = [&](int kb, auto par) {
+            float4 (&ac)[4] = decltype(par)::value ? an1 : an;
+            float4 (&gc)[4] = decltype(par)::value ? gn1 : gn;
+            float4 (&ax)[4] = decltype(par)::value ? an : an1;
+            float4 (&gx)[4] = decltype(par)::value ? gn : gn1;
             if (kb + 1 < NKB) {
-                c.template tape_load<false>(1, kb + 1, an);
-                c.template tape_load<true>(2, kb + 1, gn);
+                c.template tape_load<false>(1, kb + 1, ax);
+                c.template tape_load<true>(2, kb + 1, gx);
             }
             float2 da[2][4];
 #pragma unroll
@@ -615,24 +637,28 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
             }
             c.template put_block<false>(kb, da, 1.0f);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC_RSKEW) tc16_rback<0, 2>(c, kb - PHNN_TC_RSKEW, yA, yB, RbA, RbB, XA, XB);
+                if (kb >= PHNN_TC16_RSKEW) tc16_rback<0, 2>(c, kb - PHNN_TC16_RSKEW, yA, yB, RbA, RbB, XA, XB);
             }
+        };
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; kb += 2) {
+            a3_block(kb, Par<0>{});
+            a3_block(kb + 1, Par<1>{});
         }
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rback<0, 2>(c, kb, yA, yB, RbA, RbB, XA, XB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rback<0, 2>(c, kb, yA, yB, RbA, RbB, XA, XB);
         }
         c.end_feed();
     }
     // ---- B3: e2 = -2 a2 da2 w3 -> operand A of product 2 (dg1 = W2^T e2), in place; the rest of the R_net chain ----
     {
-        float4 a2n[4];
-        c.template tape_load<true>(0, 0, a2n);
+        float4 t0[4], t1[4];
+        c.template tape_load<true>(0, 0, t0);
         const uint32_t tacc = c.acc_wait();
-        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dz)[16]) {
-            float4 a2q[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) a2q[s] = a2n[s];
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dz)[16], auto par) {
+            float4 (&a2q)[4] = decltype(par)::value ? t1 : t0;
+            float4 (&a2n)[4] = decltype(par)::value ? t0 : t1;
             if (kb + 1 < NKB) c.template tape_load<true>(0, kb + 1, a2n);
             float2 e2[2][4];
 #pragma unroll
@@ -646,24 +672,23 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
             }
             c.template put_block<false>(kb, e2, 1.0f);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC_RSKEW) tc16_rback<2, 4>(c, kb - PHNN_TC_RSKEW, yA, yB, RbA, RbB, XA, XB);
+                if (kb >= PHNN_TC16_RSKEW) tc16_rback<2, 4>(c, kb - PHNN_TC16_RSKEW, yA, yB, RbA, RbB, XA, XB);
             }
         });
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC_RSKEW; kb < NKB; ++kb) tc16_rback<2, 4>(c, kb, yA, yB, RbA, RbB, XA, XB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rback<2, 4>(c, kb, yA, yB, RbA, RbB, XA, XB);
         }
         c.end_feed();
     }
     // ---- C4: the dg1 half of xbar_H ----
     {
-        float4 a1n[4];
-        c.template tape_load<true>(1, 0, a1n);
+        float4 t0[4], t1[4];
+        c.template tape_load<true>(1, 0, t0);
         const uint32_t tacc = c.acc_wait();
-        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dg)[16]) {
-            float4 ac[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) ac[s] = a1n[s];
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dg)[16], auto par) {
+            float4 (&ac)[4] = decltype(par)::value ? t1 : t0;
+            float4 (&a1n)[4] = decltype(par)::value ? t0 : t1;
             if (kb + 1 < NKB) c.template tape_load<true>(1, kb + 1, a1n);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
