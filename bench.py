@@ -589,13 +589,45 @@ def main():
             ts.append(e0.elapsed_time(e1))
         rms = float(np.median(ts))
         r_tflops = Bp * Tp * 73360 / (rms * 1e-3) / 1e12
+        # the same job on the latency kernel (the route of small batches), for the record
+        fwd_min = pkp.get_option("tensor_fwd_min_batch")
+        lat_ms = None
+        if fwd_min > 0:
+            pkp.set_option("tensor_fwd_min_batch", 0)
+            for _ in range(2):
+                _rollout(pkp, xp, Up, 0.05, "rk4")
+            torch.cuda.synchronize()
+            tl = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _rollout(pkp, xp, Up, 0.05, "rk4")
+                e1.record()
+                torch.cuda.synchronize()
+                tl.append(e0.elapsed_time(e1))
+            lat_ms = float(np.median(tl))
+            pkp.set_option("tensor_fwd_min_batch", fwd_min)
+        on_tc = fwd_min > 0 and Bp >= fwd_min
+        # parity sample of the timed route: first 64 instances, first 10 steps, against the CPU oracle
+        r_par = None
+        if not args.no_parity:
+            from oracle.phnn_oracle import OracleModel
+            tr_g = _rollout(pkp, xp, Up, 0.05, "rk4")
+            tr_g = (tr_g[0] if isinstance(tr_g, (tuple, list)) else tr_g)[:64, :11].cpu().numpy()
+            tr_o = OracleModel(sdp, "phnn").rollout(xp[:64].cpu().numpy(), Up[:64, :10].cpu().numpy(), 0.05, "rk4")
+            r_par = {"n": 64, "steps": 10, "traj_rel": float(np.abs(tr_g - tr_o).max() / np.abs(tr_o).max()), "tol": 1e-4}
         rollout_metric = {"metric": "phnn_rk4_rollout_instance_steps_per_s", "value": Bp * Tp / (rms * 1e-3), "unit": "instance-steps/s",
                           "ms": rms, "config": "BASELINE cfg2: pendulum pHNN (shipped weights, h=64, learned G), 4096 initial states x H=100, "
-                                               "RK4, dt 0.05, one launch (latency kernel, FP32 FMA)",
-                          "roofline": {"bound": "fp32-fma", "achieved": r_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                                       "frac": r_tflops / fp32_peak, "algorithmic_flops_per_launch": Bp * Tp * 73360,
-                                       "note": "latency-bound: 4096 instances x 100 sequential steps x 4 stages = 28 instances "
-                                               "per SM; 3.0e10 FLOP is 0.4 ms at the FP32 peak (SURVEY 8d)"}}
+                                               "RK4, dt 0.05, one launch (%s)" % (
+                                                   "phnn_tc16_kernel<PHNN_GNET,2,64>: forward-only tcgen05 instantiation, 3 x FP16 hi/lo products, "
+                                                   "32 tiles of 128 instances on 32 SMs" if on_tc else "latency kernel, FP32 FMA"),
+                          "latency_kernel_ms": lat_ms, "parity_sample": r_par,
+                          "roofline": {"bound": "latency (400 sequential evaluations per tile)", "achieved": r_tflops, "peak": fp32_peak,
+                                       "unit": "TFLOP/s", "frac": r_tflops / fp32_peak, "algorithmic_flops_per_launch": Bp * Tp * 73360,
+                                       "note": "4096 instances are 32 tiles: 32 of 148 SMs run 100 steps x 4 stages one after the other "
+                                               "(%.1f us per evaluation of a tile); the same launch takes the same time up to 18944 "
+                                               "instances (148 tiles). frac = algorithmic FLOP/s over the FP32-FMA rate measured in "
+                                               "this run" % (rms * 1e3 / (Tp * 4))}}
     except Exception as ex:  # the headline line must still be printed
         rollout_metric = {"error": repr(ex)}
 

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphnn_mpc.so")
 SOURCES = ["phnn_capi.cu"]
-DEPS = ["phnn_capi.cu", "phnn_kernel.cuh", "phnn_tc_kernel.cuh", "phnn_lat_kernel.cuh", os.path.join("..", "..", "include", "phnn_mpc.h")]
+DEPS = ["phnn_capi.cu", "phnn_kernel.cuh", "phnn_tc_kernel.cuh", "phnn_tc16_kernel.cuh", "phnn_lat_kernel.cuh", os.path.join("..", "..", "include", "phnn_mpc.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -25,6 +25,7 @@ struct phnn_pack {
                           // product, 1 = plain TF32
     long tc_min_batch;    // smallest B routed to the tcgen05 kernel
     long lat_max_batch;   // largest B routed to the one-CTA-per-instance latency kernel (0 = never)
+    long tc_fwd_min_batch;  // forward-only tcgen05 shapes: smallest B of a forward job (forward / rollout / cost) routed there (0 = never)
     float* d_small;
     float* d_big;
     unsigned char* d_wtc;
@@ -64,6 +65,12 @@ extern "C" int phnn_version(void) { return 100; }
 #define PHNN_TC_SHAPES(X) X(MK_PHNN, 4, 256)
 #define PHNN_LAT_SHAPES(X) X(MK_PHNN, 4, 64)
 #endif
+#ifdef PHNN_DEV_CFG2  // fast experiment builds: only the pendulum shape (BASELINE cfg2)
+#define PHNN_SHAPES(X) X(MK_PHNN_GNET, 2, 64)
+#define PHNN_TC_SHAPES(X)
+#define PHNN_LAT_SHAPES(X) X(MK_PHNN_GNET, 2, 64)
+#define PHNN_TC16_FWD_SHAPES(X) X(MK_PHNN_GNET, 2, 64)
+#endif
 #ifndef PHNN_SHAPES
 #define PHNN_SHAPES(X) \
     X(MK_PHNN, 4, 64)  \
@@ -85,6 +92,26 @@ extern "C" int phnn_version(void) { return 100; }
     X(MK_CANON, 4, 128)   \
     X(MK_CANON, 4, 256)
 #endif
+
+// forward-only instantiations of the second-generation tcgen05 kernel (forward evaluation, rollouts, cost without
+// gradient): the n = 2 pHNN with fixed or learned G (pendulum model, BASELINE cfg2)
+#ifndef PHNN_TC16_FWD_SHAPES
+#ifdef PHNN_DEV_CFG4
+#define PHNN_TC16_FWD_SHAPES(X)
+#else
+#define PHNN_TC16_FWD_SHAPES(X) \
+    X(MK_PHNN, 2, 64)          \
+    X(MK_PHNN_GNET, 2, 64)
+#endif
+#endif
+static bool has_tc16_fwd_shape(int mk, int n, int h) {
+    (void)mk; (void)n; (void)h;
+#define X(MK, NS, HID) \
+    if (mk == MK && n == NS && h == HID) return true;
+    PHNN_TC16_FWD_SHAPES(X)
+#undef X
+    return false;
+}
 
 static bool has_tc_shape(int mk, int n, int h) {
 #define X(MK, NS, HID) \
@@ -288,6 +315,30 @@ static void fill_tc16_small(const phnn_model_desc* d, const Tc16Scales& sc, std:
     }
 }
 
+// n = 2 forward-only records (layout in Tc16Shape): field f, pair P -> float4 at (f * h/2 + P)
+static void fill_tc16_small_n2(const phnn_model_desc* d, const Tc16Scales& sc, std::vector<float>& s) {
+    const int h = d->h, np = h / 2;
+    const bool gnet = d->learned_G != 0;
+    s.assign((size_t)(gnet ? 8 : 6) * np * 4, 0.f);
+    auto at = [&](int f, int P, int half, int o) -> float& { return s[((size_t)f * np + P) * 4 + half * 2 + o]; };
+    const float SD = pow2f(sc.eD);
+    for (int k = 0; k < h; ++k) {
+        const int P = k >> 1, o = k & 1;
+        at(0, P, 0, o) = d->W1[k * 2 + 0];  at(0, P, 1, o) = d->W1[k * 2 + 1];
+        at(1, P, 0, o) = d->b1[k];          at(1, P, 1, o) = d->b2[k];
+        at(2, P, 0, o) = d->W3[k] * SD;     at(2, P, 1, o) = d->br1[k];
+        at(3, P, 0, o) = d->Wr1[k * 2 + 0]; at(3, P, 1, o) = d->Wr1[k * 2 + 1];
+        at(4, P, 0, o) = d->Wr2[(size_t)0 * h + k];
+        at(4, P, 1, o) = 0.5f * (d->Wr2[(size_t)1 * h + k] + d->Wr2[(size_t)2 * h + k]);
+        at(5, P, 0, o) = d->Wr2[(size_t)3 * h + k];
+        if (gnet) {
+            at(5, P, 1, o) = d->bg1[k];
+            at(6, P, 0, o) = d->Wg1[k * 2 + 0]; at(6, P, 1, o) = d->Wg1[k * 2 + 1];
+            at(7, P, 0, o) = d->Wg2[(size_t)0 * h + k]; at(7, P, 1, o) = d->Wg2[(size_t)1 * h + k];
+        }
+    }
+}
+
 template <class SH>
 static void fill_small(const phnn_model_desc* d, std::vector<float>& s) {
     constexpr int NS = SH::NS, HID = SH::HID, NN = SH::NN;
@@ -340,6 +391,12 @@ static cudaError_t set_smem_limits(int mk, int n, int h) {
         e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                  (int)Tc16Shape<MK, NS, HID>::SMEM_BYTES);
     PHNN_TC_SHAPES(X)
+#undef X
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                 (int)Tc16Shape<MK, NS, HID>::SMEM_BYTES);
+    PHNN_TC16_FWD_SHAPES(X)
 #undef X
 #define X(MK, NS, HID)                                                                                                  \
     if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
@@ -431,6 +488,27 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         pk->tc_mode = 4;
         pk->tc_min_batch = 1;  // measured: the tcgen05 kernel beats the FP32-FMA kernel at every batch size (tools/gpu_crossover.py)
     }
+    if (e == cudaSuccess && has_tc16_fwd_shape(mk, n, h)) {
+        std::vector<unsigned char> w16;
+        std::vector<float> s16;
+        const Tc16Scales sc = tc16_scales(d);
+        fill_tc16_big(d, sc, w16);
+        fill_tc16_small_n2(d, sc, s16);
+        e = cudaMalloc(&pk->d_wtc16, w16.size());
+        if (e == cudaSuccess) e = cudaMemcpy(pk->d_wtc16, w16.data(), w16.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&pk->d_small16, s16.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(pk->d_small16, s16.data(), s16.size() * sizeof(float), cudaMemcpyHostToDevice);
+        pk->base.s16[0] = pow2f(-(sc.eA + sc.eB));
+        pk->base.s16[1] = pow2f(-(sc.eD + sc.eB));
+        pk->base.s16[2] = pow2f(-sc.eB);
+        pk->base.s16[4] = pow2f(sc.eA);
+        pk->base.s16[5] = pow2f(-sc.eD);
+        pk->tc_mode = 4;
+        // one 128-instance tile per CTA runs its evaluations one after the other, so a forward job takes the same time
+        // from 1 to 148 tiles (1.9 ms for 100 RK4 steps); the latency kernel (8 instances per CTA, 1.0 ms per wave of 8 per SM) is faster below ~12 instances per SM
+        // (tools/gpu_crossover.py, measured on B200)
+        pk->tc_fwd_min_batch = 12L * pk->num_sms;
+    }
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         cudaFree(pk->d_small);
@@ -465,6 +543,11 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         if (n == 4)
             for (int a = 0; a < 4; ++a)
                 for (int b = a; b < 4; ++b) P.bsym[sym_idx(a, b)] = 0.5f * (d->br2[a * 4 + b] + d->br2[b * 4 + a]);
+        if (n == 2) {  // packed 00 01 11 (forward-only tcgen05 shapes)
+            P.bsym[0] = d->br2[0];
+            P.bsym[1] = 0.5f * (d->br2[1] + d->br2[2]);
+            P.bsym[2] = d->br2[3];
+        }
     }
     if (mk == MK_PHNN_GNET)
         for (int a = 0; a < n; ++a) P.bg2[a] = d->bg2[a];
@@ -493,12 +576,19 @@ extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) 
     if (!pk || !key) return fail(PHNN_E_ARG, "phnn_pack_set_option: null argument");
     if (!strcmp(key, "tensor_mode")) {
         if (value < 0 || value > 4) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1, 2, 3 or 4");
-        if (value != 0 && !pk->d_wtc) return fail(PHNN_E_UNSUPPORTED, "no tcgen05 kernel for this model shape");
+        if (value != 0 && !pk->d_wtc && !(value == 4 && pk->d_wtc16))
+            return fail(PHNN_E_UNSUPPORTED, "no tcgen05 kernel for this model shape");
         pk->tc_mode = (int)value;
         return 0;
     }
     if (!strcmp(key, "tensor_min_batch")) {
         pk->tc_min_batch = value;
+        return 0;
+    }
+    if (!strcmp(key, "tensor_fwd_min_batch")) {
+        if (value > 0 && !has_tc16_fwd_shape(pk->mk, pk->n, pk->h))
+            return fail(PHNN_E_UNSUPPORTED, "no forward-only tcgen05 kernel for this model shape");
+        pk->tc_fwd_min_batch = value;
         return 0;
     }
     if (!strcmp(key, "latency_max_batch")) {
@@ -521,6 +611,7 @@ extern "C" long phnn_pack_get_option(const phnn_pack* pk, const char* key) {
     if (!strcmp(key, "tensor_mode")) return pk->tc_mode;
     if (!strcmp(key, "tensor_min_batch")) return pk->tc_min_batch;
     if (!strcmp(key, "latency_max_batch")) return pk->lat_max_batch;
+    if (!strcmp(key, "tensor_fwd_min_batch")) return pk->tc_fwd_min_batch;
     return -1;
 }
 
@@ -635,12 +726,40 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     return 0;
 }
 
+// forward-only shapes on the second-generation tcgen05 kernel: one CTA per 128-instance tile, nothing taped
+template <class SH16>
+static int launch_tc16_fwd_shape(const phnn_pack*, KParams& P, cudaStream_t stream) {
+    P.tc_split = 4;
+    P.ng = 1;
+    P.dbg = nullptr;
+    P.tiles = (P.B + SH16::TM - 1) / SH16::TM;
+    P.sched = nullptr;
+    P.tape = nullptr;
+    P.scratch = nullptr;
+    phnn_tc16_kernel<SH16::MK, SH16::NS, SH16::HID><<<(unsigned)P.tiles, SH16::THREADS, SH16::SMEM_BYTES, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static bool forward_only_job(const KParams& P) {
+    return P.mode == MODE_FORWARD || P.mode == MODE_ROLLOUT || (P.mode == MODE_COSTGRAD && !P.want_grad);
+}
+
 static int launch(const phnn_pack* pk, KParams& P, void* stream) {
     if (P.B <= 0) return 0;
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));
     if (prev != pk->device) CUDA_TRY(cudaSetDevice(pk->device));
     int rc = fail(PHNN_E_UNSUPPORTED, "no kernel instantiation");
+    // forward jobs of the n = 2 models: tensor cores from a few instances per SM upwards
+    if (pk->tc_mode == 4 && !pk->d_wtc && pk->d_wtc16 && pk->tc_fwd_min_batch > 0 && P.B >= pk->tc_fwd_min_batch &&
+        forward_only_job(P) && has_tc16_fwd_shape(pk->mk, pk->n, pk->h)) {
+#define X(MK, NS, HID) \
+    if (pk->mk == MK && pk->n == NS && pk->h == HID) rc = launch_tc16_fwd_shape<Tc16Shape<MK, NS, HID>>(pk, P, (cudaStream_t)stream);
+        PHNN_TC16_FWD_SHAPES(X)
+#undef X
+        if (prev != pk->device) cudaSetDevice(prev);
+        return rc;
+    }
     // small batches: one CTA per instance (latency path)
     if (pk->lat_max_batch > 0 && P.B <= pk->lat_max_batch && has_lat_shape(pk->mk, pk->n, pk->h)) {
 #define X(MK, NS, HID) \

@@ -40,19 +40,28 @@ namespace phnn {
 
 template <int MK_, int NS_, int HID_>
 struct Tc16Shape {
-    static_assert((MK_ == MK_PHNN || MK_ == MK_CANON) && NS_ == 4, "tensor-core path: cart-pole pHNN (fixed G) and canonical pHNN, n = 4");
+    // full instantiations (forward + adjoint): cart-pole pHNN with fixed G and canonical pHNN, n = 4.  Forward-only
+    // instantiations (forward evaluation, rollouts, cost without gradient): n = 2 pHNN with fixed or learned G (the
+    // pendulum model of BASELINE cfg2, src/pHNN.py:86-92)
+    static_assert(((MK_ == MK_PHNN || MK_ == MK_CANON) && NS_ == 4) || ((MK_ == MK_PHNN || MK_ == MK_PHNN_GNET) && NS_ == 2),
+                  "tensor-core path: n = 4 pHNN (fixed G) / canonical pHNN, or forward-only n = 2 pHNN");
     static constexpr int MK = MK_, NS = NS_, HID = HID_, NN = NS * NS;
+    static constexpr bool FWD_ONLY = (NS_ != 4);
+    static constexpr bool HAS_GNET = (MK_ == MK_PHNN_GNET);
 #ifdef PHNN_TC16_EXP_NOR  // timing experiment (wrong results): no R_net work
     static constexpr bool HAS_R = false;
 #else
     static constexpr bool HAS_R = (MK != MK_CANON);
 #endif
     static constexpr int TM = 128;            // instances per tile (UMMA M)
-    static_assert(HID / 32 >= PHNN_TC16_RSKEW, "R_net skew exceeds the number of K-blocks");
+    static_assert(FWD_ONLY || HID / 32 >= PHNN_TC16_RSKEW, "R_net skew exceeds the number of K-blocks");
     static constexpr int NEW = 8;             // element warps: (TMEM lane quadrant, 16-lane half)
     static constexpr int NKB = HID / 32;      // K-blocks of 32 hidden units
     static constexpr int NP = HID / 2;        // pairs of adjacent hidden units
     static constexpr int B_TILE = HID * 128;  // bytes of the weight tile of one K-block: rows of [b_hi (32 fp16) | b_lo (32 fp16)]
+#ifndef PHNN_TC16_CPF
+#define PHNN_TC16_CPF 1  // blocks by which the tape loads of the short loops (grad H, dg1 half of xbar) run ahead
+#endif
 #ifndef PHNN_TC16_NBE
 #define PHNN_TC16_NBE 5
 #endif
@@ -63,7 +72,10 @@ struct Tc16Shape {
     //   F0 {W1[.][0]} {W1[.][1]}   F1 {W1[.][2]} {W1[.][3]}   F2 {b1} {br1}   F3 {b2} {w3 * S_delta}   F4 {-2 w3 * S_e} {0}
     //   F5 {Wr1[.][0]} {Wr1[.][1]} F6 {Wr1[.][2]} {Wr1[.][3]}
     //   F7..F11 the 10 symmetrised R_net output weights (Wr2[ab][.] + Wr2[ba][.])/2, a <= b, two per field
-    static constexpr int NF = HAS_R ? 12 : 5;
+    // n = 2 (forward only):
+    //   G0 {W1[.][0]} {W1[.][1]}   G1 {b1} {b2}   G2 {w3 * S_delta} {br1}   G3 {Wr1[.][0]} {Wr1[.][1]}
+    //   G4 {Wr2s[00]} {Wr2s[01]}   G5 {Wr2s[11]} {bg1}   G6 {Wg1[.][0]} {Wg1[.][1]}   G7 {Wg2[0][.]} {Wg2[1][.]}
+    static constexpr int NF = FWD_ONLY ? (HAS_GNET ? 8 : 6) : (HAS_R ? 12 : 5);
     static constexpr int SMALL = NF * NP * 4;  // floats
     // shared memory map (bytes): barriers in [0, 256), TMEM address at 512, scheduler slot at 768
     static constexpr int OFF_B = 1024;
@@ -105,6 +117,29 @@ __device__ __forceinline__ void tmem_st_pairs(uint32_t taddr, const uint32_t (&q
         "r"(q[11]), "r"(q[12]), "r"(q[13]), "r"(q[14]), "r"(q[15])
         : "memory");
 }
+// mbarrier wait of the single-lane roles (MMA issuer, weight producer).  PHNN_TC16_WAIT_HINT > 0 passes a suspend-time
+// hint (ns) to mbarrier.try_wait: the lane is parked by the hardware until the phase completes or the hint expires,
+// instead of re-polling every ~15 cycles (ncu: SYNCS.TRYWAIT + BRA + YIELD of those two lanes were 20 % of all issued
+// warp instructions, taken from the issue slots of schedulers 0 and 1 which also host four of the element warps)
+#ifndef PHNN_TC16_WAIT_HINT
+#define PHNN_TC16_WAIT_HINT 0
+#endif
+__device__ __forceinline__ void mbar_wait_aux(uint64_t* bar, uint32_t parity) {
+#if PHNN_TC16_WAIT_HINT > 0
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)PHNN_TC16_WAIT_HINT)
+            : "memory");
+    } while (!ok);
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 // parity of a K-block as a type: the bodies of the block loops are instantiated for even and odd blocks, so buffers that
 // are filled one block ahead (tape prefetch) ping-pong between two register sets instead of being copied
 template <int P> struct Par { static constexpr int value = P; };
@@ -122,6 +157,29 @@ __device__ __forceinline__ void for_acc_frags(uint32_t tacc, F&& body) {
         tmem_wait(rb);
         if (b + 2 < NKB) tmem_ld_frag_issue(tacc + (b + 2) * 32, ra);
         body(b + 1, rb, Par<1>{});
+    }
+}
+// same, in groups of four blocks: the body gets the block index modulo 4 as a type (rotating prefetch buffers that
+// run two blocks ahead)
+template <int NKB, class F>
+__device__ __forceinline__ void for_acc_frags4(uint32_t tacc, F&& body) {
+    static_assert(NKB % 4 == 0, "blocks are visited in groups of four");
+    uint32_t ra[16], rb[16];
+    tmem_ld_frag_issue(tacc, ra);
+#pragma unroll 1
+    for (int b = 0; b < NKB; b += 4) {
+        tmem_wait(ra);
+        tmem_ld_frag_issue(tacc + (b + 1) * 32, rb);
+        body(b, ra, Par<0>{});
+        tmem_wait(rb);
+        tmem_ld_frag_issue(tacc + (b + 2) * 32, ra);
+        body(b + 1, rb, Par<1>{});
+        tmem_wait(ra);
+        tmem_ld_frag_issue(tacc + (b + 3) * 32, rb);
+        body(b + 2, ra, Par<2>{});
+        tmem_wait(rb);
+        if (b + 4 < NKB) tmem_ld_frag_issue(tacc + (b + 4) * 32, ra);
+        body(b + 3, rb, Par<3>{});
     }
 }
 // (already scaled) pair -> fp16x2 hi and fp16x2 lo = fp16(t - hi); element .x sits in the low half (even K index)
@@ -153,6 +211,8 @@ __device__ __forceinline__ float2 tanh16(float2 x) {
 }
 
 template <class SH> struct Tc16Ctx;
+template <class SH>
+__device__ __forceinline__ void tc16_eval_fwd2(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[2], float u, float (&f)[2], float& Hval);
 template <class SH>
 __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
 template <class SH>
@@ -245,18 +305,33 @@ struct Tc16Ctx {
     __device__ __forceinline__ void begin_unit(const KParams& p, long long) {
         sck = scratch ? scratch + (size_t)p.T * p.S * NS * TW : nullptr;
     }
-    __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[4], float u, float (&f)[4], float& H) {
-        tc16_eval_fwd(*this, p, y, u, f, H);
+    __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
+        if constexpr (SH::FWD_ONLY) tc16_eval_fwd2(*this, p, y, u, f, H);
+        else tc16_eval_fwd(*this, p, y, u, f, H);
     }
-    __device__ __forceinline__ void eval_vjp(const KParams& p, const float (&y)[4], float u, const float (&v)[4],
-                                             float (&xbar)[4], float& ubar) {
-        tc16_eval_vjp(*this, p, y, u, v, xbar, ubar);
+    __device__ __forceinline__ void eval_vjp(const KParams& p, const float (&y)[NS], float u, const float (&v)[NS],
+                                             float (&xbar)[NS], float& ubar) {
+        if constexpr (SH::FWD_ONLY) {
+            // forward-only instantiation: the host never routes a job with an adjoint here
+            asm volatile("trap;");
+#pragma unroll
+            for (int i = 0; i < NS; ++i) xbar[i] = 0.f;
+            ubar = 0.f;
+        } else {
+            tc16_eval_vjp(*this, p, y, u, v, xbar, ubar);
+        }
     }
 };
 
 // pair (k of this lane's four) of K-block kb: units 32 kb + 8 k + 2 cq, +1
 template <class SH>
-__device__ __forceinline__ int tc16_pair(const Tc16Ctx<SH>& c, int kb, int k) { return kb * 16 + k * 4 + c.cq; }
+__device__ __forceinline__ int tc16_pair(const Tc16Ctx<SH>& c, int kb, int k) {
+#ifdef PHNN_TC16_EXP_HALFLDS  // timing experiment (wrong results): pairs k and k^1 use the same records, loaded once (the
+                              // shared-memory volume a thread with four instances instead of two would have)
+    return kb * 16 + (k & ~1) * 4 + c.cq;
+#endif
+    return kb * 16 + k * 4 + c.cq;
+}
 // the pair of units k of a tape float4 slot pair (slots 2 rsel, 2 rsel + 1 hold k = 0,1 and k = 2,3)
 __device__ __forceinline__ float2 tape_pair(const float4 (&t)[4], int rsel, int k) {
     const float4& q = t[2 * rsel + (k >> 1)];
@@ -392,6 +467,18 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
         const float isg = p.s16[1];
         if (c.tape) {
             // a1 comes back from the tape (written by this thread in phase A, still in L2)
+#if PHNN_TC16_CPF == 2
+            // a1 two blocks ahead (a block of this loop is ~300 cycles, an L2 hit more than that)
+            float4 tb[4][4];
+            c.template tape_load<false>(1, 0, tb[0]);
+            c.template tape_load<false>(1, 1, tb[1]);
+            const uint32_t tacc = c.acc_wait();
+            for_acc_frags4<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16], auto par) {
+                constexpr int PI = decltype(par)::value;
+                float4 (&ac)[4] = tb[PI];
+                if (kb + 2 < NKB) c.template tape_load<false>(1, kb + 2, tb[(PI + 2) & 3]);
+                float2 g[2][4];
+#else
             float4 t0[4], t1[4];
             c.template tape_load<false>(1, 0, t0);
             const uint32_t tacc = c.acc_wait();
@@ -400,6 +487,7 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
                 float4 (&an)[4] = decltype(par)::value ? t0 : t1;
                 if (kb + 1 < NKB) c.template tape_load<false>(1, kb + 1, an);
                 float2 g[2][4];
+#endif
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int P = tc16_pair(c, kb, k);
@@ -473,6 +561,145 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
             }
             f[a] = s + p.Gv[a] * u;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// n = 2 (forward only): pHNN with fixed or learned G (src/pHNN.py:52-100; G_net branch :86-92)
+// ---------------------------------------------------------------------------------------
+// libdevice tanhf for both halves: a forward-only job is a long chain of evaluations of one tile (100 RK4 steps in cfg2),
+// paced by latency, not by instruction count, and its horizon error is what the rollout parity bound measures
+__device__ __forceinline__ float2 tanh_fwd2(float2 x) { return make_float2(tanhf(x.x), tanhf(x.y)); }
+__device__ __forceinline__ float2 pair_affine2(const float4& w01, const float (&x)[2], float2 b) {
+    return fma2(zw(w01), bc2(x[1]), fma2(xy(w01), bc2(x[0]), b));
+}
+// R_net (3 symmetrised sums 00 01 11) and G_net (2 sums) hidden layers + output partial sums for pairs [K0, K1)
+template <int K0, int K1, class SH>
+__device__ __forceinline__ void tc16_aux2(const Tc16Ctx<SH>& c, int kb, const float (&yA)[2], const float (&yB)[2], float2 (&SA)[5],
+                                          float2 (&SB)[5]) {
+    const float4* F = c.fields();
+#pragma unroll
+    for (int k = K0; k < K1; ++k) {
+        const int P = tc16_pair(c, kb, k);
+        const float4 g2 = F[2 * SH::NP + P], g3 = F[3 * SH::NP + P], g4 = F[4 * SH::NP + P], g5 = F[5 * SH::NP + P];
+        const float2 rA = tanh_fwd2(pair_affine2(g3, yA, zw(g2)));
+        const float2 rB = tanh_fwd2(pair_affine2(g3, yB, zw(g2)));
+        SA[0] = fma2(xy(g4), rA, SA[0]); SA[1] = fma2(zw(g4), rA, SA[1]); SA[2] = fma2(xy(g5), rA, SA[2]);
+        SB[0] = fma2(xy(g4), rB, SB[0]); SB[1] = fma2(zw(g4), rB, SB[1]); SB[2] = fma2(xy(g5), rB, SB[2]);
+        if constexpr (SH::HAS_GNET) {
+            const float4 g6 = F[6 * SH::NP + P], g7 = F[7 * SH::NP + P];
+            const float2 qA = tanh_fwd2(pair_affine2(g6, yA, zw(g5)));
+            const float2 qB = tanh_fwd2(pair_affine2(g6, yB, zw(g5)));
+            SA[3] = fma2(xy(g7), qA, SA[3]); SA[4] = fma2(zw(g7), qA, SA[4]);
+            SB[3] = fma2(xy(g7), qB, SB[3]); SB[4] = fma2(zw(g7), qB, SB[4]);
+        }
+        sched_fence();
+    }
+}
+template <class SH>
+__device__ __forceinline__ void tc16_eval_fwd2(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[2], float u, float (&f)[2],
+                                               float& Hval) {
+    constexpr int NKB = SH::NKB, NP = SH::NP;
+    const float4* F = c.fields();
+    float zA[2], zB[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { zA[i] = c.fromA(y[i]); zB[i] = c.fromB(y[i]); }
+    float2 SA[5], SB[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { SA[i] = make_float2(0.f, 0.f); SB[i] = make_float2(0.f, 0.f); }
+    // ---- phase A: a1 = tanh(W1 z + b1) -> operand A of product 1; then the first half of the auxiliary nets, which
+    //      covers the tail of the product ----
+    static_assert(NKB == 2, "a1 of the whole evaluation is kept in registers between phases A and C");
+    float2 a1s[NKB][2][4];
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int P = tc16_pair(c, kb, k);
+            const float4 g0 = F[P];
+            const float2 b1 = xy(F[NP + P]);
+            a1s[kb][0][k] = tanh_fwd2(pair_affine2(g0, zA, b1));
+            a1s[kb][1][k] = tanh_fwd2(pair_affine2(g0, zB, b1));
+            if (k & 1) sched_fence();
+        }
+        c.template put_block<true>(kb, a1s[kb], p.s16[4]);
+    }
+#pragma unroll 1
+    for (int kb = 0; kb < NKB; ++kb) tc16_aux2<0, 2>(c, kb, zA, zB, SA, SB);
+    c.end_feed();
+    // ---- phase B: a2, H, delta2 -> operand A of product 2, in place; second half of the auxiliary nets ----
+    float Hown;
+    {
+        const uint32_t tacc = c.acc_wait();
+        const float isz = p.s16[0];
+        float2 HpA = make_float2(0.f, 0.f), HpB = make_float2(0.f, 0.f);
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&zr)[16], auto) {
+            float2 d[2][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int P = tc16_pair(c, kb, k);
+                const float2 b2 = zw(F[NP + P]), w3s = xy(F[2 * NP + P]);
+#pragma unroll
+                for (int rsel = 0; rsel < 2; ++rsel) {
+                    const float2 t = tanh_fwd2(fma2(frag2(zr, k, rsel), bc2(isz), b2));
+                    if (rsel) HpB = fma2(w3s, t, HpB); else HpA = fma2(w3s, t, HpA);
+                    d[rsel][k] = mul2(one_minus_sq(t), w3s);
+                }
+                if (k & 1) sched_fence();
+            }
+            c.template put_block<false>(kb, d, 1.0f);
+        });
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb) tc16_aux2<2, 4>(c, kb, zA, zB, SA, SB);
+        c.end_feed();
+        Hown = c.quad_own_sum(HpA.x + HpA.y, HpB.x + HpB.y) * p.s16[5];
+    }
+    // ---- phase C: dH = W1^T (s1 * g1), a1 still in registers (no adjoint follows, nothing is taped) ----
+    float dH[2];
+    {
+        float2 GA[2], GB[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { GA[i] = make_float2(0.f, 0.f); GB[i] = make_float2(0.f, 0.f); }
+        const uint32_t tacc = c.acc_wait();
+        for_acc_frags<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&gr)[16], auto par) {
+            constexpr int KB = decltype(par)::value;  // NKB == 2: the block index is its parity
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int P = tc16_pair(c, kb, k);
+                const float4 g0 = F[P];
+                const float2 tA = mul2(one_minus_sq(a1s[KB][0][k]), frag2(gr, k, 0));
+                const float2 tB = mul2(one_minus_sq(a1s[KB][1][k]), frag2(gr, k, 1));
+                GA[0] = fma2(xy(g0), tA, GA[0]); GA[1] = fma2(zw(g0), tA, GA[1]);
+                GB[0] = fma2(xy(g0), tB, GB[0]); GB[1] = fma2(zw(g0), tB, GB[1]);
+                if (k & 1) sched_fence();
+            }
+        });
+        const float isg = p.s16[1];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) dH[i] = c.quad_own_sum(GA[i].x + GA[i].y, GB[i].x + GB[i].y) * isg;
+        tc_fence_before();
+    }
+    float Sp[5];
+#pragma unroll
+    for (int i = 0; i < (SH::HAS_GNET ? 5 : 3); ++i) Sp[i] = c.quad_own_sum(SA[i].x + SA[i].y, SB[i].x + SB[i].y);
+    Hval = Hown + p.b3;
+    // f = (J - J^T - S S^T) grad H + G u,  S = (R_raw + R_raw^T) / 2 (src/pHNN.py:76-100)
+    float S[2][2];
+    S[0][0] = Sp[0] + p.bsym[0];
+    S[0][1] = S[1][0] = Sp[1] + p.bsym[1];
+    S[1][1] = Sp[2] + p.bsym[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        float s = 0.f;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            float Rab = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) Rab = fmaf(S[a][k], S[b][k], Rab);
+            s = fmaf(p.Jm[a * 2 + b] - Rab, dH[b], s);
+        }
+        const float Ga = SH::HAS_GNET ? Sp[3 + a] + p.bg2[a] : p.Gv[a];
+        f[a] = s + Ga * u;
     }
 }
 
@@ -683,6 +910,16 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
     }
     // ---- C4: the dg1 half of xbar_H ----
     {
+#if PHNN_TC16_CPF == 2
+        float4 tb[4][4];
+        c.template tape_load<true>(1, 0, tb[0]);
+        c.template tape_load<true>(1, 1, tb[1]);
+        const uint32_t tacc = c.acc_wait();
+        for_acc_frags4<NKB>(c.tl16 + tacc, [&](int kb, const uint32_t (&dg)[16], auto par) {
+            constexpr int PI = decltype(par)::value;
+            float4 (&ac)[4] = tb[PI];
+            if (kb + 2 < NKB) c.template tape_load<true>(1, kb + 2, tb[(PI + 2) & 3]);
+#else
         float4 t0[4], t1[4];
         c.template tape_load<true>(1, 0, t0);
         const uint32_t tacc = c.acc_wait();
@@ -690,6 +927,7 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
             float4 (&ac)[4] = decltype(par)::value ? t1 : t0;
             float4 (&a1n)[4] = decltype(par)::value ? t0 : t1;
             if (kb + 1 < NKB) c.template tape_load<true>(1, kb + 1, a1n);
+#endif
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int P = tc16_pair(c, kb, k);
@@ -828,9 +1066,9 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID>::THREADS, 1) phnn_tc16_
                     const uint32_t afeed = tbase + (par ^ 1u) * HID;
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
-                        mbar_wait(&bars[SH::B_AFULL + kb], par);
+                        mbar_wait_aux(&bars[SH::B_AFULL + kb], par);
                         const uint32_t e = bent % SH::NBE;
-                        mbar_wait(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
+                        mbar_wait_aux(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
                         tc_fence_after();
                         const uint32_t b_t = b_base + e * SH::B_TILE;
                         const uint32_t a_hi = afeed + kb * 32, a_lo = a_hi + 16;
@@ -891,7 +1129,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID>::THREADS, 1) phnn_tc16_
                             }
                         }
                         const uint32_t e = bent % SH::NBE;
-                        mbar_wait(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u);
+                        mbar_wait_aux(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u);
                         mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
                         bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)kb * SH::B_TILE, SH::B_TILE, &bars[SH::B_BFULL + e]);
                         ++bent;

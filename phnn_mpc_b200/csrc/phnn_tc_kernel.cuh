@@ -148,7 +148,11 @@ __device__ __forceinline__ float tanh_tc(float x) {
 }
 // keeps the compiler from hoisting the next chunk's loads above this point: without it ptxas
 // front-loads a whole K-block of weight loads and then serialises the tanh chains on one register
+#if defined(PHNN_TC16_EXP_HALFLDS) || defined(PHNN_TC16_EXP_WEAKFENCE)
+__device__ __forceinline__ void sched_fence() { asm volatile(""); }  // lets the duplicate loads of the experiment merge
+#else
 __device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
+#endif
 // asynchronous TMEM load of N (16 or 8) consecutive columns of this thread's lane; the registers are
 // valid only after tmem_wait (which also ties them to the wait for the compiler)
 __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[16]) {

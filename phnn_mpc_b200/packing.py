@@ -110,7 +110,9 @@ class PackedModel:
         return cls({k: torch.from_numpy(v) for k, v in sd.items()}, device=device)
 
     def set_option(self, key, value):
-        """kernel selection knobs: 'tensor_mode' (0 FP32-FMA, 2 tcgen05 TF32 + BF16 correction (default), 3 tcgen05 3xTF32, 1 tcgen05 TF32), 'tensor_min_batch'"""
+        """kernel selection knobs (include/phnn_mpc.h): 'tensor_mode' (0 FP32-FMA, 4 tcgen05 3 x FP16 hi/lo with A in TMEM
+        (default), 2 tcgen05 TF32 + BF16 correction, 3 tcgen05 3xTF32, 1 tcgen05 TF32), 'tensor_min_batch',
+        'tensor_fwd_min_batch' (n = 2 models: forward-only tcgen05 kernel), 'latency_max_batch'"""
         _lib.check(_lib.lib().phnn_pack_set_option(ctypes.c_void_p(self.handle), key.encode(), int(value)),
                    "phnn_pack_set_option")
 

@@ -21,4 +21,8 @@ for wl in (sys.argv[1:] or ["small", "cfg4_rk4"]):
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); mpc.solve(x0); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-    print("%s %-9s %.2f ms (%.1f k solves/s)" % (os.environ.get("PHNN_MPC_LIB", "default"), wl, np.median(ts), B / np.median(ts)), flush=True)
+    out = mpc.solve(x0)
+    torch.cuda.synchronize()
+    U = out["U"].double()
+    print("%s %-9s %.2f ms (%.1f k solves/s)  checksum U %.9e |U| %.9e" % (os.path.basename(os.environ.get("PHNN_MPC_LIB", "default")), wl, np.median(ts),
+          B / np.median(ts), U.sum().item(), U.abs().sum().item()), flush=True)
