@@ -433,12 +433,13 @@ def main():
                "note": "pinned x0 -> device, solve (+ exchange), U of the whole job and this rank's costs -> pinned host, "
                        "wall clock per step, max over ranks, L2 flushed between steps"}
 
-    # ---- side measurement: plain TF32 (tensor_mode 1), the looser stated-tolerance path north_star permits ----
+    # ---- side measurement: one FP16 product per algorithmic product (tensor_mode 5), the looser stated-tolerance path
+    #      north_star permits for a reduced-precision tensor-core path; NOT the headline ----
     alt = None
     tmode = pk.get_option("tensor_mode")
-    uses_tc = tmode in (1, 2, 3, 4) and B >= pk.get_option("tensor_min_batch")
-    if uses_tc and tmode != 1 and not args.no_alt:
-        pk.set_option("tensor_mode", 1)
+    uses_tc = tmode in (1, 2, 3, 4, 5) and B >= pk.get_option("tensor_min_batch")
+    if uses_tc and tmode != 5 and not args.no_alt:
+        pk.set_option("tensor_mode", 5)
         for _ in range(2):
             mpc.solve(x0)
         ats = []
@@ -455,8 +456,10 @@ def main():
         t = torch.tensor([a_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        alt = {"label": "tensor_mode=1: plain TF32 products (NOT the headline; looser stated tolerance 2e-4 cost / 1e-3 dJ/dU, "
-                        "north_star allows a stated looser bound for a TF32 path)", "ms_per_step": float(t.item()),
+        alt = {"label": "tensor_mode=5: second-generation tcgen05 kernel with ONE FP16 product per algorithmic product "
+                        "(operands rounded to FP16, a third of the tensor work; NOT the headline; looser stated tolerance "
+                        "2e-4 cost / 1e-3 dJ/dU, north_star allows a stated looser bound for a reduced-precision path)",
+               "ms_per_step": float(t.item()),
                "value": B * world / (float(t.item()) / 1e3), "unit": "solves/s (solve kernel only, no exchange)",
                "U_maxabs_vs_headline_mode": float((o1["U"] - out["U"]).abs().max().item()),
                "best_cost_rel_vs_headline_mode": float(((o1["best_cost"] - out["best_cost"]).abs().max() /
@@ -521,13 +524,13 @@ def main():
         # mode 1 as 1 TF32 MMA.  BF16 MMAs run at twice the TF32 rate, so the time at peak rate is counted in TF32 units.
         tiles = (B + 127) // 128
         base = tiles * iters * H * S * (2 + 2) * 2.0 * 128 * h * h
-        tf32_flops = base * (3 if tmode == 3 else 1) if tmode != 4 else 0.0
+        tf32_flops = base * (3 if tmode == 3 else 1) if tmode < 4 else 0.0
         # 16-bit MMAs (twice the TF32 rate): mode 2 one BF16 product of twice the depth; mode 4 three FP16 products
         # (a_hi b_hi + a_hi b_lo + a_lo b_hi), operand A read from tensor memory
-        bf16_flops = base * 2 if tmode == 2 else (base * 3 if tmode == 4 else 0.0)
+        bf16_flops = base * 2 if tmode == 2 else (base * 3 if tmode == 4 else (base if tmode == 5 else 0.0))
         mma_flops = tf32_flops + bf16_flops
         tf32_equiv_flops = tf32_flops + bf16_flops / 2
-        scheme = {4: "3 x FP16 hi/lo products, A in TMEM (FP32-level accuracy)", 3: "3xTF32 error-compensated",
+        scheme = {5: "1 x FP16 product, A in TMEM (looser stated tolerance)", 4: "3 x FP16 hi/lo products, A in TMEM (FP32-level accuracy)", 3: "3xTF32 error-compensated",
                   2: "TF32 + BF16 correction product (FP32-level accuracy)", 1: "plain TF32"}[tmode]
         # HBM side of the same kernel: the activation tape (a1, a2, g1: 3 h floats per instance and evaluation) is
         # written by the forward sweep and read back by the adjoint
@@ -538,7 +541,7 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, this pool)" if peaks else
                                    "fallback 1400 (B200_PROFILING.md)",
                     "algorithmic_flops_per_launch": algo,
-                    "kernel": ("phnn_tc16_kernel<MK,NS,HID> (tcgen05 kind::f16, %s), one launch per step" % scheme) if tmode == 4 else
+                    "kernel": ("phnn_tc16_kernel<MK,NS,HID> (tcgen05 kind::f16, %s), one launch per step" % scheme) if tmode >= 4 else
                               "phnn_tc_kernel<MK,NS,HID> (tcgen05 kind::tf32%s, %s), one launch per step" % (
                                   " + kind::f16" if tmode == 2 else "", scheme),
                     "kernel_ms": kernel_ms,
@@ -553,6 +556,7 @@ def main():
                             "measured_dram_bytes_per_launch": traffic},
                     "note": ("FP32-level accuracy on the tensor cores costs three FP16 products per algorithmic product (hi/lo "
                              "split operands): frac vs the bf16 peak is bounded by 1/3; " if tmode == 4 else
+                             "one FP16 product per algorithmic product (tensor_mode 5, looser stated tolerance); " if tmode == 5 else
                              "FP32-level accuracy on the tensor cores costs one TF32 product (half the bf16 rate) plus a BF16 "
                              "correction product of twice the depth: frac vs the bf16 peak is bounded by 1/4; ") +
                             "the adjoint reads the forward activations from an HBM tape instead of recomputing them (4 tensor "
@@ -644,11 +648,11 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
-            "kernel_path": {4: "tcgen05-3xFP16-A-in-TMEM", 3: "tcgen05-3xTF32", 2: "tcgen05-TF32+BF16corr", 1: "tcgen05-TF32"}[tmode] if uses_tc else "fp32-fma",
+            "kernel_path": {5: "tcgen05-1xFP16-A-in-TMEM", 4: "tcgen05-3xFP16-A-in-TMEM", 3: "tcgen05-3xTF32", 2: "tcgen05-TF32+BF16corr", 1: "tcgen05-TF32"}[tmode] if uses_tc else "fp32-fma",
             "exchange": {"kind": gather_kind, "ms": gather_ms,
                          "note": "issued once per step, inside every timed step; `ms` is the exchange alone, warmed, median of 7"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity, "tf32_mode1": alt,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity, "fp16_mode5": alt,
             "rollout": rollout_metric, "step_ms": step_ms}
     print(json.dumps(line))
     if world > 1:

@@ -80,7 +80,9 @@ int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
  *   "tensor_mode"      0: FP32-FMA kernel only; 4 (default where built): second-generation tcgen05 kernel, three FP16
  *                      hi/lo products with operand A in tensor memory (FP32-level accuracy); 2: first-generation
  *                      kernel, TF32 product + one BF16 correction product (FP32-level accuracy); 3: 3xTF32 error
- *                      compensation (FP32-level accuracy, 1.5x the tensor work of 2); 1: plain TF32 (looser).
+ *                      compensation (FP32-level accuracy, 1.5x the tensor work of 2); 1: plain TF32 (looser);
+ *                      5: the second-generation kernel with ONE FP16 product per algorithmic product (operands
+ *                      rounded to FP16, a third of the tensor work of 4; looser: 2e-4 on costs, 1e-3 on dJ/dU).
  *   "tensor_min_batch" smallest B routed to the tcgen05 kernel (default 1: it beats the FP32-FMA kernel
  *                      at every batch size; small batches go to the latency kernel first).
  *   "tensor_fwd_min_batch" n = 2 pHNN models (fixed or learned G, hidden 64: the pendulum model): smallest B of a

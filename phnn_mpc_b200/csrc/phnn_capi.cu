@@ -394,6 +394,12 @@ static cudaError_t set_smem_limits(int mk, int n, int h) {
 #undef X
 #define X(MK, NS, HID)                                                                                                  \
     if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)Tc16Shape<MK, NS, HID>::SMEM_BYTES);
+    PHNN_TC_SHAPES(X)
+#undef X
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
         e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                  (int)Tc16Shape<MK, NS, HID>::SMEM_BYTES);
     PHNN_TC16_FWD_SHAPES(X)
@@ -575,7 +581,7 @@ extern "C" int phnn_pack_destroy(phnn_pack* pk) {
 extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) {
     if (!pk || !key) return fail(PHNN_E_ARG, "phnn_pack_set_option: null argument");
     if (!strcmp(key, "tensor_mode")) {
-        if (value < 0 || value > 4) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1, 2, 3 or 4");
+        if (value < 0 || value > 5) return fail(PHNN_E_ARG, "tensor_mode must be 0, 1, 2, 3, 4 or 5");
         if (value != 0 && !pk->d_wtc && !(value == 4 && pk->d_wtc16))
             return fail(PHNN_E_UNSUPPORTED, "no tcgen05 kernel for this model shape");
         pk->tc_mode = (int)value;
@@ -685,7 +691,7 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
     static_assert((3 * SH::HID * 128 * 4) % 65536 == 0, "tape prefetch granularity");
     const long long tiles = (P.B + SH::TM - 1) / SH::TM;
     using SH16 = Tc16Shape<SH::MK, SH::NS, SH::HID>;
-    const bool gen2 = pk->tc_mode == 4;  // FP16 hi/lo operands, A in tensor memory (phnn_tc16_kernel.cuh)
+    const bool gen2 = pk->tc_mode >= 4;  // FP16 operands, A in tensor memory (phnn_tc16_kernel.cuh): 4 = hi/lo, three products; 5 = one product
     P.tc_split = pk->tc_mode;  // 1 plain TF32, 2 TF32 + BF16 correction product, 3 3xTF32
     if (pk->tc_mode == 2) P.wtc = pk->d_wtc2;
     P.ng = 1;
@@ -718,7 +724,9 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
             CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
         }
     }
-    if (gen2)
+    if (gen2 && pk->tc_mode == 5)
+        phnn_tc16_kernel<SH::MK, SH::NS, SH::HID, true><<<(unsigned)grid, SH16::THREADS, SH16::SMEM_BYTES, stream>>>(P);
+    else if (gen2)
         phnn_tc16_kernel<SH::MK, SH::NS, SH::HID><<<(unsigned)grid, SH16::THREADS, SH16::SMEM_BYTES, stream>>>(P);
     else
         phnn_tc_kernel<SH::MK, SH::NS, SH::HID><<<(unsigned)grid, SH::THREADS, SH::SMEM_BYTES, stream>>>(P);

@@ -251,12 +251,13 @@ def tc_env(env):
 
 
 @pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256", "canonical"])
-@pytest.mark.parametrize("mode", [4, 3, 2, 1])
+@pytest.mark.parametrize("mode", [4, 3, 2, 1, 5])
 def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
-    # modes 3 (3xTF32) and 2 (TF32 + BF16 correction product) are held to the FP32 tolerances, mode 1 (plain TF32) to its own
+    # modes 4 (3 x FP16 hi/lo), 3 (3xTF32) and 2 (TF32 + BF16 correction product) are held to the FP32 tolerances; mode 1
+    # (plain TF32) and mode 5 (one FP16 product: 11-bit operands like TF32) to the stated looser ones
     ops, get_tc = tc_env
     z, sd, pk = get_tc(name, mode)
-    step_tol, hor_tol, grad_tol, u_fac = (STEP_TOL, HORIZON_TOL, HORIZON_TOL, 0.02) if mode != 1 else (2e-3, 2e-4, 1e-3, 0.05)
+    step_tol, hor_tol, grad_tol, u_fac = (STEP_TOL, HORIZON_TOL, HORIZON_TOL, 0.02) if mode not in (1, 5) else (2e-3, 2e-4, 1e-3, 0.05)
     dx, H = ops.forward(pk.handle, cu(z["rand_x"]), cu(z["rand_u"]))
     assert rel_err(dx.cpu().numpy(), z["rand_dx"]) < step_tol
     assert rel_err(H.cpu().numpy(), z["rand_H"]) < step_tol
