@@ -624,14 +624,15 @@ def main():
                           "ms": rms, "config": "BASELINE cfg2: pendulum pHNN (shipped weights, h=64, learned G), 4096 initial states x H=100, "
                                                "RK4, dt 0.05, one launch (%s)" % (
                                                    "phnn_tc16_kernel<PHNN_GNET,2,64>: forward-only tcgen05 instantiation, 3 x FP16 hi/lo products, "
-                                                   "32 tiles of 128 instances on 32 SMs" if on_tc else "latency kernel, FP32 FMA"),
+                                                   + ("64 tiles of 64 instances on 64 SMs" if pkp.get_option("tensor_fwd_sparse") == 1 and Bp <= 64 * 148
+                                                      else "32 tiles of 128 instances on 32 SMs") if on_tc else "latency kernel, FP32 FMA"),
                           "latency_kernel_ms": lat_ms, "parity_sample": r_par,
                           "roofline": {"bound": "latency (400 sequential evaluations per tile)", "achieved": r_tflops, "peak": fp32_peak,
                                        "unit": "TFLOP/s", "frac": r_tflops / fp32_peak, "algorithmic_flops_per_launch": Bp * Tp * 73360,
-                                       "note": "4096 instances are 32 tiles: 32 of 148 SMs run 100 steps x 4 stages one after the other "
-                                               "(%.1f us per evaluation of a tile); the same launch takes the same time up to 18944 "
-                                               "instances (148 tiles). frac = algorithmic FLOP/s over the FP32-FMA rate measured in "
-                                               "this run" % (rms * 1e3 / (Tp * 4))}}
+                                       "note": "one CTA per tile runs 100 steps x 4 stages one after the other (%.1f us per evaluation "
+                                               "of a tile); the same launch takes the same time up to one tile per SM (9472 instances on "
+                                               "64-instance tiles, 18944 on 128-instance tiles in 1.9 ms). frac = algorithmic FLOP/s over "
+                                               "the FP32-FMA rate measured in this run" % (rms * 1e3 / (Tp * 4))}}
     except Exception as ex:  # the headline line must still be printed
         rollout_metric = {"error": repr(ex)}
 

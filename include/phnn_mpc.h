@@ -87,8 +87,10 @@ int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
  *                      at every batch size; small batches go to the latency kernel first).
  *   "tensor_fwd_min_batch" n = 2 pHNN models (fixed or learned G, hidden 64: the pendulum model): smallest B of a
  *                      forward-only job (phnn_forward, phnn_rollout, phnn_cost_grad without dJdU) routed to the
- *                      forward-only instantiation of the second-generation tcgen05 kernel (default 12 x SM count by
+ *                      forward-only instantiation of the second-generation tcgen05 kernel (default 10 x SM count by
  *                      measured crossover against the latency kernel; 0 disables it; needs "tensor_mode" 4).
+ *   "tensor_fwd_sparse" the same kernel runs jobs of up to 64 instances per SM on 64-instance tiles (TMEM lanes 0..15 of
+ *                      every quadrant; twice the SMs, 1.5 instead of 1.9 ms for 100 RK4 steps): 1 (default) / 0.
  *   "latency_max_batch" largest B routed to the latency kernel (one thread per hidden unit, up to 8 instances
  *                      per CTA; default 8-96 x SM count by measured crossover, where built: hidden width <= 128;
  *                      0 disables it).                                                                                   */

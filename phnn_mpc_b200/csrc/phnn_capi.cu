@@ -26,6 +26,7 @@ struct phnn_pack {
     long tc_min_batch;    // smallest B routed to the tcgen05 kernel
     long lat_max_batch;   // largest B routed to the one-CTA-per-instance latency kernel (0 = never)
     long tc_fwd_min_batch;  // forward-only tcgen05 shapes: smallest B of a forward job (forward / rollout / cost) routed there (0 = never)
+    int tc_fwd_sparse;      // forward-only tcgen05 shapes: 64-instance tiles while they fit one per SM (1, default) or always 128 (0)
     float* d_small;
     float* d_big;
     unsigned char* d_wtc;
@@ -406,6 +407,12 @@ static cudaError_t set_smem_limits(int mk, int n, int h) {
 #undef X
 #define X(MK, NS, HID)                                                                                                  \
     if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)Tc16Shape<MK, NS, HID, false, true>::SMEM_BYTES);
+    PHNN_TC16_FWD_SHAPES(X)
+#undef X
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
         e = cudaFuncSetAttribute(phnn_lat_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                  (int)LatShape<MK, NS, HID>::SMEM_BYTES);
     PHNN_LAT_SHAPES(X)
@@ -510,10 +517,12 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         pk->base.s16[4] = pow2f(sc.eA);
         pk->base.s16[5] = pow2f(-sc.eD);
         pk->tc_mode = 4;
-        // one 128-instance tile per CTA runs its evaluations one after the other, so a forward job takes the same time
-        // from 1 to 148 tiles (1.9 ms for 100 RK4 steps); the latency kernel (8 instances per CTA, 1.0 ms per wave of 8 per SM) is faster below ~12 instances per SM
-        // (tools/gpu_crossover.py, measured on B200)
-        pk->tc_fwd_min_batch = 12L * pk->num_sms;
+        // one tile per CTA runs its evaluations one after the other, so a forward job takes the same time whatever the
+        // number of tiles up to one per SM: 1.5 ms for 100 RK4 steps on 64-instance tiles (up to 64 instances per SM),
+        // 1.9 ms on 128-instance tiles.  The latency kernel (8 instances per CTA, 1.0 ms per wave of 8 per SM) is faster
+        // below ~10 instances per SM (tools/gpu_cfg2_tc.py, measured on B200)
+        pk->tc_fwd_min_batch = 10L * pk->num_sms;
+        pk->tc_fwd_sparse = 1;
     }
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
@@ -597,6 +606,10 @@ extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) 
         pk->tc_fwd_min_batch = value;
         return 0;
     }
+    if (!strcmp(key, "tensor_fwd_sparse")) {
+        pk->tc_fwd_sparse = value != 0;
+        return 0;
+    }
     if (!strcmp(key, "latency_max_batch")) {
         if (value > 0 && !has_lat_shape(pk->mk, pk->n, pk->h)) return fail(PHNN_E_UNSUPPORTED, "no latency kernel for this model shape");
         pk->lat_max_batch = value;
@@ -618,6 +631,7 @@ extern "C" long phnn_pack_get_option(const phnn_pack* pk, const char* key) {
     if (!strcmp(key, "tensor_min_batch")) return pk->tc_min_batch;
     if (!strcmp(key, "latency_max_batch")) return pk->lat_max_batch;
     if (!strcmp(key, "tensor_fwd_min_batch")) return pk->tc_fwd_min_batch;
+    if (!strcmp(key, "tensor_fwd_sparse")) return pk->tc_fwd_sparse;
     return -1;
 }
 
@@ -736,14 +750,24 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
 
 // forward-only shapes on the second-generation tcgen05 kernel: one CTA per 128-instance tile, nothing taped
 template <class SH16>
-static int launch_tc16_fwd_shape(const phnn_pack*, KParams& P, cudaStream_t stream) {
+static int launch_tc16_fwd_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream) {
     P.tc_split = 4;
     P.ng = 1;
     P.dbg = nullptr;
-    P.tiles = (P.B + SH16::TM - 1) / SH16::TM;
     P.sched = nullptr;
     P.tape = nullptr;
     P.scratch = nullptr;
+    // 64-instance (sparse) tiles while they still fit one per SM: twice the SMs for the same job, half the instruction
+    // stream per tile; 128-instance tiles beyond that
+    using SP = Tc16Shape<SH16::MK, SH16::NS, SH16::HID, false, true>;
+    const long long tiles64 = (P.B + SP::TM - 1) / SP::TM;
+    if (pk->tc_fwd_sparse && tiles64 <= pk->num_sms) {
+        P.tiles = tiles64;
+        phnn_tc16_kernel<SH16::MK, SH16::NS, SH16::HID, false, true><<<(unsigned)P.tiles, SP::THREADS, SP::SMEM_BYTES, stream>>>(P);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    P.tiles = (P.B + SH16::TM - 1) / SH16::TM;
     phnn_tc16_kernel<SH16::MK, SH16::NS, SH16::HID><<<(unsigned)P.tiles, SH16::THREADS, SH16::SMEM_BYTES, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -38,8 +38,15 @@ namespace phnn {
 #define PHNN_TC16_RSKEW 3
 #endif
 
-template <int MK_, int NS_, int HID_, bool LOWP_ = false>
+template <int MK_, int NS_, int HID_, bool LOWP_ = false, bool SPARSE_ = false>
 struct Tc16Shape {
+    // SPARSE (forward-only shapes, jobs of at most 64 instances per SM): a tile holds 64 instances in TMEM lanes 0..15 of
+    // every quadrant, and the two warps of a quadrant split the K-blocks instead of the 16-lane halves.  A forward job is
+    // a chain of evaluations bound by the instructions its tile issues (ncu: schedulers 68 % busy on the 32 SMs that
+    // 4096 instances occupy with 128-row tiles); half the instances per tile put it on twice the SMs with all four
+    // schedulers of each still busy (TMEM lane quadrant = warp % 4 = scheduler).  The MMA still computes 128 rows.
+    static constexpr bool SPARSE = SPARSE_;
+    static_assert(!SPARSE_ || (NS_ != 4 && HID_ == 64), "sparse tiles: forward-only shapes with two K-blocks");
     // LOWP (tensor_mode 5): one FP16 product per algorithmic product -- operands rounded to FP16 (11-bit significand), no
     // lo halves, a third of the tensor work; looser, stated tolerance (tests/test_gpu_parity.py).  Not the default.
     static constexpr bool LOWP = LOWP_;
@@ -56,7 +63,7 @@ struct Tc16Shape {
 #else
     static constexpr bool HAS_R = (MK != MK_CANON);
 #endif
-    static constexpr int TM = 128;            // instances per tile (UMMA M)
+    static constexpr int TM = SPARSE_ ? 64 : 128;  // instances per tile (UMMA M is 128 either way)
     static_assert(FWD_ONLY || HID / 32 >= PHNN_TC16_RSKEW, "R_net skew exceeds the number of K-blocks");
     // element warps: (TMEM lane quadrant, 16-lane half).  (Splitting the K-blocks of the forward-only shapes over twice as
     // many warps was measured SLOWER -- 2.18 vs 1.93 ms on cfg2: that chain is bound by the instructions its tile issues,
@@ -86,7 +93,8 @@ struct Tc16Shape {
     // shared memory map (bytes): barriers in [0, 256), TMEM address at 512, scheduler slot at 768
     static constexpr int OFF_B = 1024;
     static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE;
-    static constexpr int SMEM_BYTES = OFF_SMALL + SMALL * 4;
+    static constexpr int OFF_XCH = OFF_SMALL + SMALL * 4;  // sparse tiles: [evaluation parity][K-block owner][64 instances][8 floats]
+    static constexpr int SMEM_BYTES = OFF_XCH + (SPARSE_ ? 2 * 2 * 64 * 8 * 4 : 0);
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static constexpr int B_AFULL = 0, B_BFULL = NKB, B_BEMPTY = NKB + NBE, B_ACC = NKB + 2 * NBE, B_SMALL = B_ACC + 2;
     static_assert((B_SMALL + 1) * 8 <= 256, "barriers live in the first 256 bytes");
@@ -226,6 +234,8 @@ template <class SH> struct Tc16Ctx;
 template <class SH>
 __device__ __forceinline__ void tc16_eval_fwd2(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[2], float u, float (&f)[2], float& Hval);
 template <class SH>
+__device__ __forceinline__ void tc16_eval_fwd2s(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[2], float u, float (&f)[2], float& Hval);
+template <class SH>
 __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u, float (&f)[4], float& Hval);
 template <class SH>
 __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[4], float u, const float (&v)[4],
@@ -241,6 +251,7 @@ struct Tc16Ctx {
     int lane, cq;    // lane; position in the quad (lanes of a quad share two instances: A = TMEM lane base + lane/4, B = A + 8)
     int srcA, srcB;  // lanes whose own instance is A / B of this quad
     int tid;         // element thread index (tape layout)
+    int ksel, slot, xpar;  // sparse tiles: K-block of this warp, instance index in the tile, parity of the exchange buffer
     uint32_t tl16;   // TMEM base address with the lane offset of this warp's 16-lane block
     uint32_t qdone;  // products whose accumulator this thread has waited for
     uint32_t qfeed;  // products this thread has fed (operand A written for)
@@ -330,7 +341,8 @@ struct Tc16Ctx {
         sck = scratch ? scratch + (size_t)p.T * p.S * NS * TW : nullptr;
     }
     __device__ __forceinline__ void eval_fwd(const KParams& p, const float (&y)[NS], float u, float (&f)[NS], float& H) {
-        if constexpr (SH::FWD_ONLY) tc16_eval_fwd2(*this, p, y, u, f, H);
+        if constexpr (SH::SPARSE) tc16_eval_fwd2s(*this, p, y, u, f, H);
+        else if constexpr (SH::FWD_ONLY) tc16_eval_fwd2(*this, p, y, u, f, H);
         else tc16_eval_fwd(*this, p, y, u, f, H);
     }
     __device__ __forceinline__ void eval_vjp(const KParams& p, const float (&y)[NS], float u, const float (&v)[NS],
@@ -746,6 +758,123 @@ __device__ __forceinline__ void tc16_eval_fwd2(Tc16Ctx<SH>& c, const KParams& p,
     }
 }
 
+// The same evaluation on a sparse tile: this warp owns K-block c.ksel of its quadrant's 16 instances; the sums over the
+// hidden dimension are completed with the warp that owns the other K-block through shared memory (one exchange and one
+// named barrier of 64 threads per evaluation; the buffers alternate, so a warp that runs ahead into the next evaluation
+// does not overwrite what its partner is still reading).  Both warps finish with bit-identical totals (IEEE addition is
+// commutative) and run the per-instance algebra redundantly, as the two owner lanes of an instance already do.
+template <class SH>
+__device__ __forceinline__ void tc16_eval_fwd2s(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[2], float u, float (&f)[2],
+                                                float& Hval) {
+    constexpr int NP = SH::NP;
+    static_assert(SH::NKB == 2, "one K-block per warp of a quadrant");
+    const float4* F = c.fields();
+    const int kb = c.ksel;
+    float zA[2], zB[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { zA[i] = c.fromA(y[i]); zB[i] = c.fromB(y[i]); }
+    float2 SA[5], SB[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { SA[i] = make_float2(0.f, 0.f); SB[i] = make_float2(0.f, 0.f); }
+    // ---- phase A ----
+    float2 a1s[2][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int P = tc16_pair(c, kb, k);
+        const float4 g0 = F[P];
+        const float2 b1 = xy(F[NP + P]);
+        a1s[0][k] = tanh_fwd2(pair_affine2(g0, zA, b1));
+        a1s[1][k] = tanh_fwd2(pair_affine2(g0, zB, b1));
+        if (k & 1) sched_fence();
+    }
+    c.template put_block<true>(kb, a1s, p.s16[4]);
+    tc16_aux2<0, 2>(c, kb, zA, zB, SA, SB);
+    c.end_feed();
+    // ---- phase B ----
+    float2 HpA = make_float2(0.f, 0.f), HpB = make_float2(0.f, 0.f);
+    {
+        const uint32_t tacc = c.acc_wait();
+        const float isz = p.s16[0];
+        uint32_t zr[16];
+        tmem_ld_frag_issue(c.tl16 + tacc + kb * 32, zr);
+        tmem_wait(zr);
+        float2 d[2][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int P = tc16_pair(c, kb, k);
+            const float2 b2 = zw(F[NP + P]), w3s = xy(F[2 * NP + P]);
+#pragma unroll
+            for (int rsel = 0; rsel < 2; ++rsel) {
+                const float2 t = tanh_fwd2(fma2(frag2(zr, k, rsel), bc2(isz), b2));
+                if (rsel) HpB = fma2(w3s, t, HpB); else HpA = fma2(w3s, t, HpA);
+                d[rsel][k] = mul2(one_minus_sq(t), w3s);
+            }
+            if (k & 1) sched_fence();
+        }
+        c.template put_block<false>(kb, d, 1.0f);
+        tc16_aux2<2, 4>(c, kb, zA, zB, SA, SB);
+        c.end_feed();
+    }
+    // ---- phase C ----
+    float2 GA[2], GB[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { GA[i] = make_float2(0.f, 0.f); GB[i] = make_float2(0.f, 0.f); }
+    {
+        const uint32_t tacc = c.acc_wait();
+        uint32_t gr[16];
+        tmem_ld_frag_issue(c.tl16 + tacc + kb * 32, gr);
+        tmem_wait(gr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 g0 = F[tc16_pair(c, kb, k)];
+            const float2 tA = mul2(one_minus_sq(a1s[0][k]), frag2(gr, k, 0));
+            const float2 tB = mul2(one_minus_sq(a1s[1][k]), frag2(gr, k, 1));
+            GA[0] = fma2(xy(g0), tA, GA[0]); GA[1] = fma2(zw(g0), tA, GA[1]);
+            GB[0] = fma2(xy(g0), tB, GB[0]); GB[1] = fma2(zw(g0), tB, GB[1]);
+        }
+        tc_fence_before();
+    }
+    // ---- sums over this warp's hidden units, then over the other K-block through shared memory ----
+    float v[8];
+    v[0] = c.quad_own_sum(HpA.x + HpA.y, HpB.x + HpB.y);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) v[1 + i] = c.quad_own_sum(GA[i].x + GA[i].y, GB[i].x + GB[i].y);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[3 + i] = (i < (SH::HAS_GNET ? 5 : 3)) ? c.quad_own_sum(SA[i].x + SA[i].y, SB[i].x + SB[i].y) : 0.f;
+    {
+        float4* X = reinterpret_cast<float4*>(phnn_smem + SH::OFF_XCH);
+        float4* mine = X + ((c.xpar * 2 + c.ksel) * 64 + c.slot) * 2;
+        const float4* other = X + ((c.xpar * 2 + (c.ksel ^ 1)) * 64 + c.slot) * 2;
+        mine[0] = make_float4(v[0], v[1], v[2], v[3]);  // both owner lanes of an instance write the same values
+        mine[1] = make_float4(v[4], v[5], v[6], v[7]);
+        group_bar(1 + (int)((threadIdx.x >> 5) & 3), 64);  // the two warps of this quadrant
+        const float4 o0 = other[0], o1 = other[1];
+        v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
+        v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+        c.xpar ^= 1;
+    }
+    Hval = v[0] * p.s16[5] + p.b3;
+    const float isg = p.s16[1];
+    const float dH[2] = {v[1] * isg, v[2] * isg};
+    float S[2][2];
+    S[0][0] = v[3] + p.bsym[0];
+    S[0][1] = S[1][0] = v[4] + p.bsym[1];
+    S[1][1] = v[5] + p.bsym[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        float s = 0.f;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            float Rab = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) Rab = fmaf(S[a][k], S[b][k], Rab);
+            s = fmaf(p.Jm[a * 2 + b] - Rab, dH[b], s);
+        }
+        const float Ga = SH::HAS_GNET ? v[6 + a] + p.bg2[a] : p.Gv[a];
+        f[a] = s + Ga * u;
+    }
+}
+
 // R_net backward chain for pairs [K0, K1) of K-block kb, both instances: X += Wr1[.]^T (1 - r^2) (Wr2sym[.] . Rb)
 template <int K0, int K1, class SH>
 __device__ __forceinline__ void tc16_rback(const Tc16Ctx<SH>& c, int kb, const float (&yA)[4], const float (&yB)[4], const float (&RbA)[10],
@@ -1018,14 +1147,14 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-template <int MK, int NS, int HID, bool LOWP = false>
-__global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP>::THREADS, 1) phnn_tc16_kernel(const __grid_constant__ KParams p) {
-    using SH = Tc16Shape<MK, NS, HID, LOWP>;
+template <int MK, int NS, int HID, bool LOWP = false, bool SPARSE = false>
+__global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS, 1) phnn_tc16_kernel(const __grid_constant__ KParams p) {
+    using SH = Tc16Shape<MK, NS, HID, LOWP, SPARSE>;
     uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int e = 0; e < SH::NKB; ++e) mbar_init(&bars[SH::B_AFULL + e], SH::NEW);
+        for (int e = 0; e < SH::NKB; ++e) mbar_init(&bars[SH::B_AFULL + e], SH::SPARSE ? 4 : SH::NEW);  // warps that feed one K-block
         for (int e = 0; e < SH::NBE; ++e) {
             mbar_init(&bars[SH::B_BFULL + e], 1);
             mbar_init(&bars[SH::B_BEMPTY + e], 1);
@@ -1069,7 +1198,10 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP>::THREADS, 1) phnn
         // ===== element threads =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SH::REGS_ELEM));
         Tc16Ctx<SH> c;
-        const int quad = warp & 3, half = warp >> 2, g = lane >> 2;
+        const int quad = warp & 3, half = SH::SPARSE ? 0 : (warp >> 2), g = lane >> 2;
+        c.ksel = SH::SPARSE ? (warp >> 2) : 0;
+        c.xpar = 0;
+        c.slot = quad * 16 + g + 8 * ((lane >> 1) & 1);
         c.lane = lane;
         c.cq = lane & 3;
         c.srcA = lane & ~3;
@@ -1079,17 +1211,17 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP>::THREADS, 1) phnn
         c.tl16 = tbase + ((uint32_t)(quad * 32 + half * 16) << 16);
         c.qdone = 0;
         c.qfeed = 0;
-        c.store = (lane & 1) == 0;
+        c.store = (lane & 1) == 0 && (!SH::SPARSE || (warp >> 2) == 0);
         c.tape = tape;
         c.scratch = p.scratch ? p.scratch + (size_t)blockIdx.x * tc_scratch_floats_per_cta(NS, p.T, p.S) : nullptr;
         c.sck = nullptr;
         c.ev = 0;
         mbar_wait(&bars[SH::B_SMALL], 0);
         if (steal) {
-            run_job(c, p, ss, c.row);
+            run_job(c, p, ss, SH::SPARSE ? c.slot : c.row);
         } else {
             StridedSched sched{(long long)blockIdx.x, (long long)blockIdx.x, p.tiles, (int)gridDim.x, n_outer, 0};
-            run_job(c, p, sched, c.row);
+            run_job(c, p, sched, SH::SPARSE ? c.slot : c.row);
         }
         tc_fence_before();
     } else if (warp == SH::NEW) {

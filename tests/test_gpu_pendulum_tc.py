@@ -133,3 +133,34 @@ def test_fixed_G_pendulum_shape():
     assert rel_err(H.cpu().numpy(), Ho) < 1e-5
     tr, _ = ops.rollout(pk.handle, cu(x0), cu(U), 0.02, 1, 0)
     assert rel_err(tr.cpu().numpy(), M.rollout(x0, U, 0.02, "rk4")) < 1e-4
+
+
+def test_sparse_and_dense_tiles_agree(pend):
+    """jobs of up to 64 instances per SM run on 64-instance tiles (two warps of a TMEM quadrant split the K-blocks and add
+    their sums through shared memory), larger ones on 128-instance tiles: same results within one evaluation's rounding,
+    ragged last tiles included; a job beyond the 64-per-SM limit against the oracle"""
+    from oracle.phnn_oracle import OracleModel
+    ops, z, sd, pk = pend
+    assert pk.get_option("tensor_fwd_sparse") == 1
+    rng = np.random.default_rng(9)
+    M = OracleModel(sd, "phnn")
+    for B in (1, 63, 65, 700):
+        x0 = (rng.uniform(-1, 1, size=(B, 2)) * [2.0, 2.0]).astype(np.float32)
+        U = rng.uniform(-1, 1, size=(B, 10, 1)).astype(np.float32)
+        tr_s, en_s = ops.rollout(pk.handle, cu(x0), cu(U), 0.05, 1, 2)
+        pk.set_option("tensor_fwd_sparse", 0)
+        try:
+            tr_d, en_d = ops.rollout(pk.handle, cu(x0), cu(U), 0.05, 1, 2)
+        finally:
+            pk.set_option("tensor_fwd_sparse", 1)
+        assert rel_err(tr_s.cpu().numpy(), tr_d.cpu().numpy()) < 1e-5
+        assert rel_err(en_s.cpu().numpy(), en_d.cpu().numpy()) < 1e-5
+        tro, eno = M.rollout(x0, U, 0.05, "rk4", energy_mode=2)
+        assert rel_err(tr_s.cpu().numpy(), tro) < 1e-4
+        assert rel_err(en_s.cpu().numpy(), eno) < 1e-4
+    B = 64 * 148 + 100   # one more than fits 64 per SM on a B200: 128-instance tiles
+    x0 = (rng.uniform(-1, 1, size=(B, 2)) * [2.0, 2.0]).astype(np.float32)
+    U = rng.uniform(-1, 1, size=(B, 10, 1)).astype(np.float32)
+    tr, _ = ops.rollout(pk.handle, cu(x0), cu(U), 0.05, 1, 0)
+    sel = np.r_[0:40, B - 40:B]
+    assert rel_err(tr.cpu().numpy()[sel], M.rollout(x0[sel], U[sel], 0.05, "rk4")) < 1e-4

@@ -50,7 +50,10 @@ for B in (int(b) for b in (os.environ.get("SWEEP") or "128,256,512,1024,2048,409
     pk.set_option("latency_max_batch", 0)
     tf, _ = timeit(B)
     route(1)
+    pk.set_option("tensor_fwd_sparse", 0)
+    td, bd = timeit(B)
+    pk.set_option("tensor_fwd_sparse", 1)
     tt, b = timeit(B)
     pk.set_option("latency_max_batch", lat_default)
-    print("B=%6d x H=100 RK4: latency %.3f ms  FP32-FMA %.3f ms  tcgen05 %.3f ms  (%.1f M inst-steps/s)  max|diff| %.2e" % (B, tl, tf, tt, B * 100 / tt / 1e3,
-          (a - b).abs().max().item()), flush=True)
+    print("B=%6d x H=100 RK4: latency %.3f ms  FP32-FMA %.3f ms  tcgen05 128-row tiles %.3f ms  tcgen05 default (64-row tiles up to 9472) %.3f ms  (%.1f M inst-steps/s)  dense vs sparse max|diff| %.2e" % (
+          B, tl, tf, td, tt, B * 100 / tt / 1e3, (bd - b).abs().max().item()), flush=True)
