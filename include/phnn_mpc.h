@@ -91,6 +91,11 @@ int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
  *                      measured crossover against the latency kernel; 0 disables it; needs "tensor_mode" 4).
  *   "tensor_fwd_sparse" the same kernel runs jobs of up to 64 instances per SM on 64-instance tiles (TMEM lanes 0..15 of
  *                      every quadrant; twice the SMs, 1.5 instead of 1.9 ms for 100 RK4 steps): 1 (default) / 0.
+ *   "tensor_pair"      tensor_mode 4 solve jobs with an even number of 128-instance tiles run as clusters of two CTAs on
+ *                      the two SMs of a TPC: every tensor product is one tcgen05.mma.cta_group::2 of M = 256 over the two
+ *                      tiles of the pair, each CTA staging half of every weight tile (half the tensor-core operand-B reads
+ *                      and half the L2 -> SM weight stream per SM).  Results are bit-identical to the single-CTA launch.
+ *                      0 (default: measured +0.5 % on the power-capped full job, -1.7 % on an unthrottled slice) / 1.
  *   "latency_max_batch" largest B routed to the latency kernel (one thread per hidden unit, up to 8 instances
  *                      per CTA; default 8-96 x SM count by measured crossover, where built: hidden width <= 128;
  *                      0 disables it).                                                                                   */

@@ -18,6 +18,11 @@
 
 using namespace phnn;
 
+// CTA pairs (tcgen05 cta_group::2) for tensor_mode 4 solve jobs: option "tensor_pair"
+#ifndef PHNN_TC_PAIR_DEFAULT
+#define PHNN_TC_PAIR_DEFAULT 0
+#endif
+
 struct phnn_pack {
     int abi_kind, mk, n, m, h;
     int device, num_sms;
@@ -27,6 +32,7 @@ struct phnn_pack {
     long lat_max_batch;   // largest B routed to the one-CTA-per-instance latency kernel (0 = never)
     long tc_fwd_min_batch;  // forward-only tcgen05 shapes: smallest B of a forward job (forward / rollout / cost) routed there (0 = never)
     int tc_fwd_sparse;      // forward-only tcgen05 shapes: 64-instance tiles while they fit one per SM (1, default) or always 128 (0)
+    int tc_pair;            // tensor_mode 4 solve jobs: clusters of two CTAs sharing every weight tile (tcgen05 cta_group::2)
     float* d_small;
     float* d_big;
     unsigned char* d_wtc;
@@ -401,6 +407,13 @@ static cudaError_t set_smem_limits(int mk, int n, int h) {
 #undef X
 #define X(MK, NS, HID)                                                                                                  \
     if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
+        e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID, false, false, true>,                                     \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,                                            \
+                                 (int)Tc16Shape<MK, NS, HID, false, false, true>::SMEM_BYTES);
+    PHNN_TC_SHAPES(X)
+#undef X
+#define X(MK, NS, HID)                                                                                                  \
+    if (e == cudaSuccess && mk == MK && n == NS && h == HID)                                                            \
         e = cudaFuncSetAttribute(phnn_tc16_kernel<MK, NS, HID>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                  (int)Tc16Shape<MK, NS, HID>::SMEM_BYTES);
     PHNN_TC16_FWD_SHAPES(X)
@@ -524,6 +537,7 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         pk->tc_fwd_min_batch = 10L * pk->num_sms;
         pk->tc_fwd_sparse = 1;
     }
+    pk->tc_pair = PHNN_TC_PAIR_DEFAULT;
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         cudaFree(pk->d_small);
@@ -610,6 +624,10 @@ extern "C" int phnn_pack_set_option(phnn_pack* pk, const char* key, long value) 
         pk->tc_fwd_sparse = value != 0;
         return 0;
     }
+    if (!strcmp(key, "tensor_pair")) {
+        pk->tc_pair = value != 0;
+        return 0;
+    }
     if (!strcmp(key, "latency_max_batch")) {
         if (value > 0 && !has_lat_shape(pk->mk, pk->n, pk->h)) return fail(PHNN_E_UNSUPPORTED, "no latency kernel for this model shape");
         pk->lat_max_batch = value;
@@ -632,6 +650,7 @@ extern "C" long phnn_pack_get_option(const phnn_pack* pk, const char* key) {
     if (!strcmp(key, "latency_max_batch")) return pk->lat_max_batch;
     if (!strcmp(key, "tensor_fwd_min_batch")) return pk->tc_fwd_min_batch;
     if (!strcmp(key, "tensor_fwd_sparse")) return pk->tc_fwd_sparse;
+    if (!strcmp(key, "tensor_pair")) return pk->tc_pair;
     return -1;
 }
 
@@ -738,7 +757,23 @@ static int launch_tc_shape(const phnn_pack* pk, KParams& P, cudaStream_t stream)
             CUDA_TRY(cudaMemsetAsync(P.sched, 0, sizeof(int) * (size_t)(tiles + 1), stream));
         }
     }
-    if (gen2 && pk->tc_mode == 5)
+    // work-stealing solve jobs with an even number of tiles on at least two SMs: CTA pairs (clusters of two along x)
+    if (gen2 && pk->tc_mode == 4 && pk->tc_pair && P.sched && tiles % 2 == 0 && grid >= 2) {
+        using SHP = Tc16Shape<SH::MK, SH::NS, SH::HID, false, false, true>;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(grid & ~1LL));
+        cfg.blockDim = dim3(SHP::THREADS);
+        cfg.dynamicSmemBytes = SHP::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, phnn_tc16_kernel<SH::MK, SH::NS, SH::HID, false, false, true>, P));
+    } else if (gen2 && pk->tc_mode == 5)
         phnn_tc16_kernel<SH::MK, SH::NS, SH::HID, true><<<(unsigned)grid, SH16::THREADS, SH16::SMEM_BYTES, stream>>>(P);
     else if (gen2)
         phnn_tc16_kernel<SH::MK, SH::NS, SH::HID><<<(unsigned)grid, SH16::THREADS, SH16::SMEM_BYTES, stream>>>(P);

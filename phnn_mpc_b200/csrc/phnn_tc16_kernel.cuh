@@ -28,6 +28,8 @@
 //
 // Roles: warps 0..7 element threads, warp 8 MMA issuer (one lane), warp 9 weight producer (cp.async.bulk ring).
 #pragma once
+#include <type_traits>
+
 #include "phnn_tc_kernel.cuh"
 
 namespace phnn {
@@ -38,8 +40,17 @@ namespace phnn {
 #define PHNN_TC16_RSKEW 3
 #endif
 
-template <int MK_, int NS_, int HID_, bool LOWP_ = false, bool SPARSE_ = false>
+template <int MK_, int NS_, int HID_, bool LOWP_ = false, bool SPARSE_ = false, bool PAIR_ = false>
 struct Tc16Shape {
+    // PAIR (solve jobs with an even number of tiles): the kernel runs as clusters of two CTAs on the two SMs of a TPC and
+    // every tensor product is ONE tcgen05.mma.cta_group::2 of M = 256 over the two tiles of the pair: each CTA keeps its own
+    // 128 instances (operand A and the accumulators in its own tensor memory, element code unchanged) but stages only HALF
+    // of every weight tile (its 128 of the N = 256 rows), so the tensor-core reads of operand B on the shared-memory pipe
+    // and the L2 -> SM weight stream are halved per SM.  The leader CTA issues the MMAs; the other CTA's element warps
+    // arrive on the leader's operand barriers through the cluster window, its otherwise idle MMA warp relays "my half of
+    // the weight tile has landed", and tcgen05.commit multicasts the completion barriers to both CTAs.
+    static constexpr bool PAIR = PAIR_;
+    static_assert(!PAIR_ || (!SPARSE_ && NS_ == 4), "CTA pairs: full (forward + adjoint) shapes only");
     // SPARSE (forward-only shapes, jobs of at most 64 instances per SM): a tile holds 64 instances in TMEM lanes 0..15 of
     // every quadrant, and the two warps of a quadrant split the K-blocks instead of the 16-lane halves.  A forward job is
     // a chain of evaluations bound by the instructions its tile issues (ncu: schedulers 68 % busy on the 32 SMs that
@@ -72,13 +83,14 @@ struct Tc16Shape {
     static constexpr int NKB = HID / 32;      // K-blocks of 32 hidden units
     static constexpr int NP = HID / 2;        // pairs of adjacent hidden units
     static constexpr int B_TILE = HID * 128;  // bytes of the weight tile of one K-block: rows of [b_hi (32 fp16) | b_lo (32 fp16)]
+    static constexpr int B_TILE_CTA = PAIR_ ? B_TILE / 2 : B_TILE;  // what one CTA stages of it
 #ifndef PHNN_TC16_CPF
 #define PHNN_TC16_CPF 1  // blocks by which the tape loads of the short loops (grad H, dg1 half of xbar) run ahead
 #endif
 #ifndef PHNN_TC16_NBE
 #define PHNN_TC16_NBE 5
 #endif
-    static constexpr int NBE = (HID >= 256) ? PHNN_TC16_NBE : 8;  // weight ring entries
+    static constexpr int NBE = (HID >= 256 && !PAIR_) ? PHNN_TC16_NBE : 8;  // weight ring entries
     static constexpr int TMEM_COLS = (2 * HID <= 32) ? 32 : (2 * HID <= 64) ? 64 : (2 * HID <= 128) ? 128 : (2 * HID <= 256) ? 256 : 512;
     // small weights: field-major arrays of float4, one entry per pair P of adjacent hidden units (2P, 2P+1); every
     // half of a field is the pair {unit 2P, unit 2P+1}
@@ -92,7 +104,7 @@ struct Tc16Shape {
     static constexpr int SMALL = NF * NP * 4;  // floats
     // shared memory map (bytes): barriers in [0, 256), TMEM address at 512, scheduler slot at 768
     static constexpr int OFF_B = 1024;
-    static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE;
+    static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE_CTA;
     static constexpr int OFF_XCH = OFF_SMALL + SMALL * 4;  // sparse tiles: [evaluation parity][K-block owner][64 instances][8 floats]
     static constexpr int SMEM_BYTES = OFF_XCH + (SPARSE_ ? 2 * 2 * 64 * 8 * 4 : 0);
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -115,6 +127,95 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ----------------------------------------------------------------------
+// D[tmem of both CTAs] (+)= A[tmem of both CTAs, 128 rows each] * B[smem descriptor, half of the N rows in each CTA]
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// completion of all MMAs issued so far -> the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// address of the same shared-memory location in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive(cta_id): what the arrival publishes is tensor-memory / async-proxy state that tcgen05.wait::st +
+// tcgen05.fence::before_thread_sync (or the bulk copy's own complete_tx) have already made complete.  A .release.cluster
+// arrive compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrival, i.e. it waits for the warp's tape
+// stores to reach L2 at every K-block hand-off: measured +30 % on the whole solve.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// Work-stealing schedule of a CTA pair: the leader pulls (pair of tiles, iteration) units from the global counter and
+// hands the unit to both CTAs; CTA r of the pair runs tile 2 k + r.  Same progress protocol per tile as StealSched.
+struct PairStealSched {
+    int* counter;
+    int* progress;
+    long long tiles;  // even
+    int iters;
+    int* slot;
+    int nelem;
+    uint32_t rank;
+    static constexpr bool kStateInWorkspace = true;
+    __device__ __forceinline__ long long tile0() const { return -1; }
+    __device__ __forceinline__ int grab() {
+        const long long npairs = tiles >> 1;
+        if (rank == 0 && threadIdx.x == 0) {
+            const int n = atomicAdd(counter, 1);
+            const long long total = npairs * iters;
+            if (n < total) {
+                const int it = (int)(n / npairs) + 1;
+                const long long tile = 2 * (n % npairs);
+                if (it > 1) {
+                    while (*reinterpret_cast<volatile int*>(progress + tile) < it - 1) __nanosleep(256);
+                    while (*reinterpret_cast<volatile int*>(progress + tile + 1) < it - 1) __nanosleep(256);
+                    __threadfence();
+                }
+            }
+            const int v = n < total ? n : -1;
+            *slot = v;
+            asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa_u32(smem_u32(slot), 1)), "r"(v) : "memory");
+        }
+        cluster_sync_all();
+        const int n = *reinterpret_cast<volatile int*>(slot);
+        cluster_sync_all();
+        return n;
+    }
+    __device__ __forceinline__ bool next(Unit& u) {
+        const int n = grab();
+        if (n < 0) return false;
+        const long long npairs = tiles >> 1;
+        u.it = (int)(n / npairs) + 1;
+        u.tile = 2 * (n % npairs) + rank;
+        return true;
+    }
+    template <class ENG>
+    __device__ __forceinline__ void done(ENG&, const Unit& u) {
+        group_bar(6, nelem);
+        if (threadIdx.x == 0) {
+            __threadfence();
+            *reinterpret_cast<volatile int*>(progress + u.tile) = u.it;
+        }
+    }
+};
 // 16 TMEM lanes x 32 columns as the mma-style fragment: r[4 k + 2 rsel + e] = (lane base + lane/4 + 8 rsel, column 8 k + 2 (lane%4) + e)
 __device__ __forceinline__ void tmem_ld_frag_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -253,6 +354,7 @@ struct Tc16Ctx {
     int tid;         // element thread index (tape layout)
     int ksel, slot, xpar;  // sparse tiles: K-block of this warp, instance index in the tile, parity of the exchange buffer
     uint32_t tl16;   // TMEM base address with the lane offset of this warp's 16-lane block
+    uint32_t afull;  // CTA pairs: address of the LEADER's operand-A barriers in the cluster window
     uint32_t qdone;  // products whose accumulator this thread has waited for
     uint32_t qfeed;  // products this thread has fed (operand A written for)
     float* sck;      // per tile: R_net sums [0,10) and grad H [10,14) of every forward evaluation, [T*S][16][128]
@@ -314,7 +416,11 @@ struct Tc16Ctx {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars()[SH::B_AFULL + kb]);
+        if constexpr (SH::PAIR) {
+            if (lane == 0) mbar_arrive_cluster(afull + 8u * (uint32_t)kb);
+        } else {
+            if (lane == 0) mbar_arrive(&bars()[SH::B_AFULL + kb]);
+        }
     }
     __device__ __forceinline__ void end_feed() { ++qfeed; }
     // float4 slot of the tape: array which (0 a2, 1 a1, 2 g1), K-block kb, slot = 2 rsel + (k >> 1)
@@ -1147,16 +1253,20 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
-template <int MK, int NS, int HID, bool LOWP = false, bool SPARSE = false>
-__global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS, 1) phnn_tc16_kernel(const __grid_constant__ KParams p) {
-    using SH = Tc16Shape<MK, NS, HID, LOWP, SPARSE>;
+template <int MK, int NS, int HID, bool LOWP = false, bool SPARSE = false, bool PAIR = false>
+__global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE, PAIR>::THREADS, 1) phnn_tc16_kernel(const __grid_constant__ KParams p) {
+    using SH = Tc16Shape<MK, NS, HID, LOWP, SPARSE, PAIR>;
     uint64_t* bars = reinterpret_cast<uint64_t*>(phnn_smem);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(phnn_smem + 512);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CTA pairs (launched as clusters of two): rank 0 is the leader that issues the MMAs of both
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) {
-        for (int e = 0; e < SH::NKB; ++e) mbar_init(&bars[SH::B_AFULL + e], SH::SPARSE ? 4 : SH::NEW);  // warps that feed one K-block
+        // warps that feed one K-block (of both CTAs of a pair: the other CTA's warps arrive on the leader's barriers)
+        for (int e = 0; e < SH::NKB; ++e) mbar_init(&bars[SH::B_AFULL + e], SH::SPARSE ? 4 : (PAIR ? 2 * SH::NEW : SH::NEW));
         for (int e = 0; e < SH::NBE; ++e) {
-            mbar_init(&bars[SH::B_BFULL + e], 1);
+            // leader of a pair: its own bulk copy + the relay of the other CTA ("my half has landed")
+            mbar_init(&bars[SH::B_BFULL + e], (PAIR && crank == 0) ? 2 : 1);
             mbar_init(&bars[SH::B_BEMPTY + e], 1);
         }
         mbar_init(&bars[SH::B_ACC + 0], 1);
@@ -1165,7 +1275,17 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == SH::NEW) {
+    if constexpr (PAIR) {
+        // barriers of both CTAs initialised before either allocates tensor memory or arrives remotely
+        __syncthreads();
+        cluster_sync_all();
+        if (warp == SH::NEW) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                         "r"((uint32_t)SH::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    } else if (warp == SH::NEW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                      "r"((uint32_t)SH::TMEM_COLS)
                      : "memory");
@@ -1173,6 +1293,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tbase = *tmem_ptr;
 
@@ -1192,7 +1313,15 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
     const long long my_tiles = p.tiles > (long long)blockIdx.x ? (p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const size_t tape_eval = (size_t)3 * HID * 128;  // floats per taped evaluation
     float* const tape = (p.tape && nadj > 0) ? p.tape + (size_t)blockIdx.x * E * tape_eval : nullptr;
-    StealSched ss{p.sched, p.sched + 1, p.tiles, p.iters, reinterpret_cast<int*>(phnn_smem + 768), 32 * SH::NEW};
+    using Steal = typename std::conditional<PAIR, PairStealSched, StealSched>::type;
+    Steal ss;
+    ss.counter = p.sched;
+    ss.progress = p.sched + 1;
+    ss.tiles = p.tiles;
+    ss.iters = p.iters;
+    ss.slot = reinterpret_cast<int*>(phnn_smem + 768);
+    ss.nelem = 32 * SH::NEW;
+    if constexpr (PAIR) ss.rank = crank;
 
     if (warp < SH::NEW) {
         // ===== element threads =====
@@ -1209,6 +1338,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
         c.row = quad * 32 + half * 16 + g + 8 * ((lane >> 1) & 1);
         c.tid = threadIdx.x;
         c.tl16 = tbase + ((uint32_t)(quad * 32 + half * 16) << 16);
+        c.afull = PAIR ? mapa_u32(smem_u32(&bars[SH::B_AFULL]), 0) : 0u;
         c.qdone = 0;
         c.qfeed = 0;
         c.store = (lane & 1) == 0 && (!SH::SPARSE || (warp >> 2) == 0);
@@ -1219,7 +1349,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
         mbar_wait(&bars[SH::B_SMALL], 0);
         if (steal) {
             run_job(c, p, ss, SH::SPARSE ? c.slot : c.row);
-        } else {
+        } else if constexpr (!PAIR) {  // pairs are launched for work-stealing solve jobs only
             StridedSched sched{(long long)blockIdx.x, (long long)blockIdx.x, p.tiles, (int)gridDim.x, n_outer, 0};
             run_job(c, p, sched, SH::SPARSE ? c.slot : c.row);
         }
@@ -1227,12 +1357,29 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
     } else if (warp == SH::NEW) {
         // ===== MMA issuer =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SH::REGS_AUX));
-        const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // F16 x F16 -> F32
+        const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);  // F16 x F16 -> F32
         const uint32_t b_base = smem_u32(phnn_smem + SH::OFF_B);
         uint32_t bent = 0;
         long long qtot = 0;  // products issued so far (accumulator / operand parity continues across units)
         for (long long unit = 0;; ++unit) {
             if (steal ? ss.grab() < 0 : unit >= my_tiles) break;
+            if constexpr (PAIR) {
+                if (crank != 0) {
+                    // the non-leader's MMA warp only relays: its half of the weight tile has landed -> leader's barrier
+                    if (lane == 0) {
+                        const uint32_t lead_bfull = mapa_u32(smem_u32(&bars[SH::B_BFULL]), 0);
+#pragma unroll 1
+                        for (long long qk = 0; qk < nprod * SH::NKB; ++qk) {
+                            const uint32_t e = bent % SH::NBE;
+                            mbar_wait_aux(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
+                            mbar_arrive_cluster(lead_bfull + 8u * e);
+                            ++bent;
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
             if (lane == 0) {
 #pragma unroll 1
                 for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
@@ -1241,25 +1388,38 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
                     const uint32_t afeed = tbase + (par ^ 1u) * HID;
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
-                        mbar_wait_aux(&bars[SH::B_AFULL + kb], par);
                         const uint32_t e = bent % SH::NBE;
+                        mbar_wait_aux(&bars[SH::B_AFULL + kb], par);
                         mbar_wait_aux(&bars[SH::B_BFULL + e], (bent / SH::NBE) & 1u);
                         tc_fence_after();
-                        const uint32_t b_t = b_base + e * SH::B_TILE;
+                        const uint32_t b_t = b_base + e * SH::B_TILE_CTA;
                         const uint32_t a_hi = afeed + kb * 32, a_lo = a_hi + 16;
                         // a_hi b_hi + a_hi b_lo + a_lo b_hi; the weight row is [b_hi (64 B) | b_lo (64 B)], K = 16 per MMA
-                        umma_f16_ts(acc, a_hi, umma_desc_sw128(b_t), idesc, kb ? 1u : 0u);
-                        umma_f16_ts(acc, a_hi + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
-                        if constexpr (!SH::LOWP) {
-                            umma_f16_ts(acc, a_hi, umma_desc_sw128(b_t + 64), idesc, 1u);
-                            umma_f16_ts(acc, a_hi + 8, umma_desc_sw128(b_t + 96), idesc, 1u);
-                            umma_f16_ts(acc, a_lo, umma_desc_sw128(b_t), idesc, 1u);
-                            umma_f16_ts(acc, a_lo + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
+                        if constexpr (PAIR) {
+                            umma_f16_ts_pair(acc, a_hi, umma_desc_sw128(b_t), idesc, kb ? 1u : 0u);
+                            umma_f16_ts_pair(acc, a_hi + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
+                            if constexpr (!SH::LOWP) {
+                                umma_f16_ts_pair(acc, a_hi, umma_desc_sw128(b_t + 64), idesc, 1u);
+                                umma_f16_ts_pair(acc, a_hi + 8, umma_desc_sw128(b_t + 96), idesc, 1u);
+                                umma_f16_ts_pair(acc, a_lo, umma_desc_sw128(b_t), idesc, 1u);
+                                umma_f16_ts_pair(acc, a_lo + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
+                            }
+                            umma_commit_pair(&bars[SH::B_BEMPTY + e]);
+                        } else {
+                            umma_f16_ts(acc, a_hi, umma_desc_sw128(b_t), idesc, kb ? 1u : 0u);
+                            umma_f16_ts(acc, a_hi + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
+                            if constexpr (!SH::LOWP) {
+                                umma_f16_ts(acc, a_hi, umma_desc_sw128(b_t + 64), idesc, 1u);
+                                umma_f16_ts(acc, a_hi + 8, umma_desc_sw128(b_t + 96), idesc, 1u);
+                                umma_f16_ts(acc, a_lo, umma_desc_sw128(b_t), idesc, 1u);
+                                umma_f16_ts(acc, a_lo + 8, umma_desc_sw128(b_t + 32), idesc, 1u);
+                            }
+                            umma_commit(&bars[SH::B_BEMPTY + e]);
                         }
-                        umma_commit(&bars[SH::B_BEMPTY + e]);
                         ++bent;
                     }
-                    umma_commit(&bars[SH::B_ACC + par]);
+                    if constexpr (PAIR) umma_commit_pair(&bars[SH::B_ACC + par]);
+                    else umma_commit(&bars[SH::B_ACC + par]);
                 }
             }
             __syncwarp();
@@ -1285,7 +1445,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
                 for (long long qq = 0; qq < nprod; ++qq, ++qtot) {
                     // adjoint products of evaluation e (descending): 0 -> da1 loop (reads a1, g1), 1 -> e2 loop (reads a2)
                     const long long qi = tape ? qq % per_iter - 2LL * nfwd : -1;
-                    const unsigned char* src = p.wtc16 + (size_t)(qtot & 1) * SH::NKB * SH::B_TILE;
+                    const unsigned char* src = p.wtc16 + (size_t)(qtot & 1) * SH::NKB * SH::B_TILE + (size_t)crank * SH::B_TILE_CTA;
 #pragma unroll 1
                     for (int kb = 0; kb < SH::NKB; ++kb) {
                         if (qi >= 0) {
@@ -1307,8 +1467,8 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
                         }
                         const uint32_t e = bent % SH::NBE;
                         mbar_wait_aux(&bars[SH::B_BEMPTY + e], ((bent / SH::NBE) & 1u) ^ 1u);
-                        mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE);
-                        bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE, src + (size_t)kb * SH::B_TILE, SH::B_TILE, &bars[SH::B_BFULL + e]);
+                        mbar_expect_tx(&bars[SH::B_BFULL + e], SH::B_TILE_CTA);
+                        bulk_g2s(phnn_smem + SH::OFF_B + e * SH::B_TILE_CTA, src + (size_t)kb * SH::B_TILE, SH::B_TILE_CTA, &bars[SH::B_BFULL + e]);
                         ++bent;
                     }
                 }
@@ -1317,7 +1477,15 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE>::THREADS,
         }
     }
     __syncthreads();
-    if (warp == SH::NEW) {
+    if constexpr (PAIR) {
+        // the leader's MMAs read the other CTA's shared and tensor memory, its barriers receive remote arrivals: neither CTA
+        // may leave (or free its tensor memory) before both are done
+        cluster_sync_all();
+        if (warp == SH::NEW) {
+            tc_fence_after();
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"((uint32_t)SH::TMEM_COLS) : "memory");
+        }
+    } else if (warp == SH::NEW) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"((uint32_t)SH::TMEM_COLS) : "memory");
     }

@@ -647,7 +647,12 @@ def test_benchmarked_config_vs_oracle(tc_env, mode):
     Q, R, ca = _cfg4_cost()
     C = M.cost_struct(Q, R, np.zeros(4), -15.0, 15.0)
     Uo, histo, besto = M.mpc_solve(C, x0, U0, 0.02, "rk4", lr=lr, iters=iters)
-    U, hist, best = ops.mpc_solve(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, lr, 0.9, 0.999, 1e-8, iters, 0, True)
+    pk.set_option("tensor_pair", 1)
+    try:
+        U, hist, best = ops.mpc_solve(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, lr, 0.9, 0.999, 1e-8, iters, 0, True)
+        torch.cuda.synchronize()
+    finally:
+        pk.set_option("tensor_pair", 0)
     assert rel_err(hist.cpu().numpy(), histo) < HORIZON_TOL
     assert rel_err(best.cpu().numpy(), besto) < HORIZON_TOL
     assert np.abs(U.cpu().numpy() - Uo).max() < 0.02 * lr + 1e-5
@@ -684,3 +689,59 @@ def test_cfg4_shape_golden_reference(tc_env, mode):
     U19, _, _ = ops.mpc_solve(pk.handle, cu(x0), cu(U0), float(z["dt"]), 1, *ca, lr, 0.9, 0.999, 1e-8, iters - 1, 0, False)
     _, g19, _ = ops.cost_grad(pk.handle, cu(x0), U19, float(z["dt"]), 1, *ca, True, False)
     assert rel_err(g19.cpu().numpy(), z["rk4_grad_last"]) < HORIZON_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# CTA pairs (option "tensor_pair", tcgen05 cta_group::2): two 128-instance tiles per cluster, one M = 256 MMA per product,
+# each CTA staging half of every weight tile.  Same MMAs per row and the same element code as the single-CTA launch, so
+# the results are required to be BIT-IDENTICAL to it -- and, independently, within the stated bounds of the oracle.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cartpole_h256", "cartpole_h128", "canonical"])
+@pytest.mark.parametrize("B,H,iters", [(256, 6, 3), (128 * 300, 4, 2), (128 * 22 - 5, 5, 2), (128 * 7, 5, 2)])
+def test_cta_pair_bit_identical_to_single(tc_env, name, B, H, iters):
+    """even tile counts run as CTA pairs (incl. more tiles than SMs and a ragged last tile); an odd tile count (7) falls
+    back to the single-CTA launch; either way the solve equals the tensor_pair = 0 solve bit for bit"""
+    ops, get_tc = tc_env
+    z, sd, pk = get_tc(name, 4)
+    rng = np.random.default_rng(B + H)
+    x0 = (rng.uniform(-1, 1, size=(B, 4)) * [1.0, 0.3, 0.5, 0.5]).astype(np.float32)
+    U0 = rng.uniform(-2, 2, size=(B, H, 1)).astype(np.float32)
+    _, _, ca = _cfg4_cost()
+    outs = []
+    try:
+        for pair in (0, 1):
+            pk.set_option("tensor_pair", pair)
+            assert pk.get_option("tensor_pair") == pair
+            U, hist, best = ops.mpc_solve(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, 0.015, 0.9, 0.999, 1e-8, iters, 1, True)
+            torch.cuda.synchronize()
+            outs.append((U.cpu().numpy(), hist.cpu().numpy(), best.cpu().numpy()))
+    finally:
+        pk.set_option("tensor_pair", 0)   # the default
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_cta_pair_benchmarked_config_vs_oracle(tc_env):
+    """bench.py's default job (hidden 256, H=50, RK4, 20 Adam iterations) on 256 of its instances through the CTA-pair
+    launch, against the CPU oracle"""
+    from oracle.phnn_oracle import OracleModel, set_threads
+    import os
+    ops, get_tc = tc_env
+    z, sd, pk = get_tc("cartpole_h256", 4)
+    set_threads(os.cpu_count() or 1)
+    M = OracleModel(sd, "phnn")
+    B, H, iters, lr = 256, 50, 20, 0.015
+    x0 = _bench_inputs(B).numpy()
+    U0 = np.zeros((B, H, 1), np.float32)
+    Q, R, ca = _cfg4_cost()
+    C = M.cost_struct(Q, R, np.zeros(4), -15.0, 15.0)
+    Uo, histo, besto = M.mpc_solve(C, x0, U0, 0.02, "rk4", lr=lr, iters=iters)
+    pk.set_option("tensor_pair", 1)
+    try:
+        U, hist, best = ops.mpc_solve(pk.handle, cu(x0), cu(U0), 0.02, 1, *ca, lr, 0.9, 0.999, 1e-8, iters, 0, True)
+        torch.cuda.synchronize()
+    finally:
+        pk.set_option("tensor_pair", 0)
+    assert rel_err(hist.cpu().numpy(), histo) < HORIZON_TOL
+    assert rel_err(best.cpu().numpy(), besto) < HORIZON_TOL
+    assert np.abs(U.cpu().numpy() - Uo).max() < 0.02 * lr + 1e-5
