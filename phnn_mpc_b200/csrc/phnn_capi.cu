@@ -241,6 +241,7 @@ static int floor_log2(float x) {  // floor(log2 x) for finite x > 0
 }
 struct Tc16Scales {
     int eB, eA, eD, eE, wexp;  // S_B = 2^eB (weights), S_a = 2^eA (a1), S_delta = 2^eD (w3 in delta2), S_e = 2^eE (w3 in e2)
+    int eRW;                   // S_RW = 2^eRW: symmetrised R_net output weights, max |Wr2sym| S_RW in [2^9, 2^10)
 };
 // Exact power-of-two scales that put every FP16 operand of the four products in [~2^-2, 2^15] (FP16: 11-bit
 // significand, normal range 6.1e-5 .. 65504; hi + lo keeps 22 bits as long as |lo| >= 6.1e-5, i.e. |x| >= 0.25):
@@ -272,6 +273,15 @@ static Tc16Scales tc16_scales(const phnn_model_desc* d) {
     s.wexp = 13 - (floor_log2(rho1) + 1);                 // rho1 2^(wexp+1) <= 2^14
     const float bound = 0.77f * maxw3 * rho2 * rho1 * pow2f(s.wexp + 1);
     s.eE = 15 - (floor_log2(bound) + 1);                  // bound 2^eE <= 2^15
+    s.eRW = 0;
+    if (d->kind == PHNN_KIND_PHNN && d->Wr2) {
+        float maxR = 1e-30f;
+        for (int a = 0; a < n; ++a)
+            for (int b = a; b < n; ++b)
+                for (int k = 0; k < h; ++k)
+                    maxR = std::fmax(maxR, std::fabs(0.5f * (d->Wr2[(size_t)(a * n + b) * h + k] + d->Wr2[(size_t)(b * n + a) * h + k])));
+        s.eRW = 9 - floor_log2(maxR);
+    }
     return s;
 }
 
@@ -300,8 +310,52 @@ static void fill_tc16_big(const phnn_model_desc* d, const Tc16Scales& sc, std::v
 static void fill_tc16_small(const phnn_model_desc* d, const Tc16Scales& sc, std::vector<float>& s) {
     const int h = d->h, n = d->n, np = h / 2;
     const bool has_r = d->kind == PHNN_KIND_PHNN;
-    s.assign((size_t)(has_r ? 12 : 5) * np * 4, 0.f);
+    // R_net models: behind the fields, the symmetrised output layer as mma.sync.m16n8k16 B fragments (FP16 hi | lo, times
+    // S_RW), one uint4 {hi(b0,b1), hi(b2,b3), lo(b0,b1), lo(b2,b3)} per lane:
+    //   forward  [kb][step][n-tile][lane]: B[kk][c] = Wr2sym[c = 8 nt + lane/4][unit 32 kb + 16 step + kk], kk = 2 t + {0,1,8,9}
+    //   backward [kb][group][lane]:        B[c][u]  = Wr2sym[c = 2 t + {0,1,8,9}][unit 32 kb + 8 group + lane/4]      (t = lane % 4)
+    const int nkb = h / 32;
+    const size_t nfield = (size_t)(has_r ? 12 : 5) * np * 4;
+    s.assign(nfield + (has_r ? (size_t)nkb * 4 * 32 * 4 * 2 : 0), 0.f);
     auto at = [&](int f, int P, int half, int o) -> float& { return s[((size_t)f * np + P) * 4 + half * 2 + o]; };
+    if (has_r) {
+        const float SR = pow2f(sc.eRW);
+        auto wsym = [&](int c, int k) -> float {
+            if (c >= 10) return 0.f;
+            int a = 0, b = 0;
+            for (int aa = 0; aa < n; ++aa)
+                for (int bb = aa; bb < n; ++bb)
+                    if (sym_idx(aa, bb) == c) { a = aa; b = bb; }
+            return SR * 0.5f * (d->Wr2[(size_t)(a * n + b) * h + k] + d->Wr2[(size_t)(b * n + a) * h + k]);
+        };
+        auto pack = [&](float lo_el, float hi_el, uint32_t& whi, uint32_t& wlo) {  // lo_el in the low 16 bits
+            const __half h0 = __float2half_rn(lo_el), h1 = __float2half_rn(hi_el);
+            const __half l0 = __float2half_rn(lo_el - __half2float(h0)), l1 = __float2half_rn(hi_el - __half2float(h1));
+            unsigned short u0, u1, v0, v1;
+            memcpy(&u0, &h0, 2); memcpy(&u1, &h1, 2); memcpy(&v0, &l0, 2); memcpy(&v1, &l1, 2);
+            whi = (uint32_t)u0 | ((uint32_t)u1 << 16);
+            wlo = (uint32_t)v0 | ((uint32_t)v1 << 16);
+        };
+        uint32_t* rf = reinterpret_cast<uint32_t*>(s.data() + nfield);
+        uint32_t* rb = rf + (size_t)nkb * 4 * 32 * 4;
+        for (int kb = 0; kb < nkb; ++kb)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3;
+                for (int step = 0; step < 2; ++step)
+                    for (int nt = 0; nt < 2; ++nt) {
+                        uint32_t* w = rf + ((((size_t)kb * 2 + step) * 2 + nt) * 32 + lane) * 4;
+                        const int c = 8 * nt + g, u0 = 32 * kb + 16 * step + 2 * t;
+                        pack(wsym(c, u0), wsym(c, u0 + 1), w[0], w[2]);
+                        pack(wsym(c, u0 + 8), wsym(c, u0 + 9), w[1], w[3]);
+                    }
+                for (int grp = 0; grp < 4; ++grp) {
+                    uint32_t* w = rb + (((size_t)kb * 4 + grp) * 32 + lane) * 4;
+                    const int u = 32 * kb + 8 * grp + g;
+                    pack(wsym(2 * t, u), wsym(2 * t + 1, u), w[0], w[2]);
+                    pack(wsym(2 * t + 8, u), wsym(2 * t + 9, u), w[1], w[3]);
+                }
+            }
+    }
     const float SD = pow2f(sc.eD), SE = pow2f(sc.eE - sc.eB);  // e2 is formed from the dz2 accumulator, which carries S_B
     for (int k = 0; k < h; ++k) {
         const int P = k >> 1, o = k & 1;
@@ -508,7 +562,9 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         pk->base.s16[4] = pow2f(sc.eA);
         pk->base.s16[5] = pow2f(-sc.eD);
         pk->base.s16[6] = pow2f(sc.eE + sc.eB);
+        pk->base.s16[7] = pow2f(-(9 + sc.eRW));
         pk->base.wexp16 = sc.wexp;
+        pk->base.rexp16 = sc.eRW;
         // default: the second-generation kernel (three FP16 products, operand A in tensor memory): FP32-level accuracy,
         // measured 1.2-1.3x the first-generation kernel's default (mode 2: TF32 + BF16 correction product)
         pk->tc_mode = 4;

@@ -93,8 +93,9 @@ struct KParams {
     const unsigned char* wtc16;  // pre-swizzled K-blocks of W2 and W2^T, rows of [b_hi (32 fp16) | b_lo (32 fp16)], scaled by S_B
     const float* wsmall16;       // field-major small-layer records (Tc16Shape)
     float s16[8];                // exact power-of-two scales: [0] 1/(S_a S_B), [1] 1/(S_delta S_B), [2] 1/S_B, [3] 1/(S_e S_B),
-                                 // [4] S_a, [5] 1/S_delta, [6] S_e S_B
+                                 // [4] S_a, [5] 1/S_delta, [6] S_e S_B, [7] 1/(2^9 S_RW) (R_net output sums on mma.sync)
     int wexp16;                  // per-instance adjoint scale: max |w'| lands in [2^wexp16, 2^(wexp16+1))
+    int rexp16;                  // S_RW = 2^rexp16, the scale of the R_net output-layer fragments
     // model constants
     float Jm[16];  // MK 0/1: J - J^T ; MK 2: the canonical J buffer
     float Gv[4];

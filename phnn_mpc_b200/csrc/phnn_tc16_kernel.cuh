@@ -40,6 +40,21 @@ namespace phnn {
 #define PHNN_TC16_RSKEW 3
 #endif
 
+// PHNN_TC16_RMMA = 1 (experiment, NOT the default): the R_net output layer (hidden -> 10 symmetrised sums, and its
+// transpose in the adjoint) as mma.sync.m16n8k16 products on the fragments the element threads already hold (the
+// tcgen05.ld.16x256b layout IS the mma.sync A / D fragment layout), three FP16 hi/lo products, instead of FFMA2 over
+// per-pair records from shared memory: 10 of the 27 record fields a pair of evaluations loads per unit pair become 2
+// (-26 % shared-memory load wavefronts, 160 FFMA2 per K-block and warp become 24 HMMA + 8 splits).  Parity unchanged
+// (profiles/r02_rnet_mma_sync_rejected.txt), but MEASURED SLOWER: 15.84 vs 13.36 ms on the profiling slice, 679 vs 623 ms
+// on cfg4.  tools/hmma_probe.cu: HMMA.16816.F32 runs at 8 cycles per instruction and scheduler, 21 cycles dependent, on an
+// otherwise idle SM, but next to the running tcgen05.mma stream the 1536 HMMAs per evaluation pair and SM cost ~10 SM
+// cycles each (a build without them, PHNN_TC16_EXP_NOHMMA, runs 12.76 ms: the HMMAs alone are 3.35 ms): the legacy path
+// serialises across the SM while the tensor cores execute tcgen05.mma.  TMEM is full at h = 256, so there is no tcgen05
+// route for these side products either; they stay on the FMA pipe.
+#ifndef PHNN_TC16_RMMA
+#define PHNN_TC16_RMMA 0
+#endif
+
 template <int MK_, int NS_, int HID_, bool LOWP_ = false, bool SPARSE_ = false, bool PAIR_ = false>
 struct Tc16Shape {
     // PAIR (solve jobs with an even number of tiles): the kernel runs as clusters of two CTAs on the two SMs of a TPC and
@@ -101,7 +116,12 @@ struct Tc16Shape {
     //   G0 {W1[.][0]} {W1[.][1]}   G1 {b1} {b2}   G2 {w3 * S_delta} {br1}   G3 {Wr1[.][0]} {Wr1[.][1]}
     //   G4 {Wr2s[00]} {Wr2s[01]}   G5 {Wr2s[11]} {bg1}   G6 {Wg1[.][0]} {Wg1[.][1]}   G7 {Wg2[0][.]} {Wg2[1][.]}
     static constexpr int NF = FWD_ONLY ? (HAS_GNET ? 8 : 6) : (HAS_R ? 12 : 5);
-    static constexpr int SMALL = NF * NP * 4;  // floats
+    // R_net output layer on mma.sync fragments (PHNN_TC16_RMMA, full shapes with an R_net): behind the fields, the B
+    // fragments of the forward sums [kb][step][n-tile][lane] and of the backward chain [kb][group][lane], one uint4 per
+    // lane each (layout: fill_tc16_small in phnn_capi.cu)
+    static constexpr bool RMMA = !FWD_ONLY && HAS_R && (PHNN_TC16_RMMA != 0);
+    static constexpr int RFRAG = NKB * 4 * 32 * 4;  // 32-bit words of one fragment array
+    static constexpr int SMALL = NF * NP * 4 + (RMMA ? 2 * RFRAG : 0);  // floats staged in shared memory
     // shared memory map (bytes): barriers in [0, 256), TMEM address at 512, scheduler slot at 768
     static constexpr int OFF_B = 1024;
     static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE_CTA;
@@ -331,6 +351,32 @@ __device__ __forceinline__ float2 tanh16(float2 x) {
 #endif
 }
 
+// tanh of a pair times S (an exact power of two): S - 2 S / (exp(2x) + 1), no extra instruction
+__device__ __forceinline__ float2 tanh16_scaled(float2 x, float S) {
+    const float2 t = mul2(x, bc2(2.8853900817779268f));
+    const float2 d = add2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), bc2(1.0f));
+    return fma2(bc2(-2.0f * S), make_float2(rcp_approx(d.x), rcp_approx(d.y)), bc2(S));
+}
+// D (16 x 8, FP32) += A (16 x 16, FP16, row) * B (16 x 8, FP16, col): the warp-level tensor-core product on register
+// fragments.  Thread (g = lane / 4, t = lane % 4): a0 = A[g][2t, 2t+1], a1 = A[g+8][2t, 2t+1], a2 = A[g][2t+8, 2t+9],
+// a3 = A[g+8][2t+8, 2t+9]; b0 = B[2t, 2t+1][g], b1 = B[2t+8, 2t+9][g]; d0,d1 = D[g][2t, 2t+1], d2,d3 = D[g+8][2t, 2t+1]
+// -- rows g / g+8 are the two instances of this thread and (2t, 2t+1) its pair of units: the tcgen05.ld.16x256b layout.
+__device__ __forceinline__ void hmma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef PHNN_TC16_EXP_NOHMMA  // timing experiment (wrong results): everything of the mma.sync path but the HMMAs themselves
+    d[0] += __uint_as_float(a[0] ^ b0); d[2] += __uint_as_float(a[1] ^ b1); d[1] += __uint_as_float(a[2]); d[3] += __uint_as_float(a[3]);
+    return;
+#endif
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// hi/lo products of one fragment pair: A B ~= Ahi Bhi + Ahi Blo + Alo Bhi   (b = {hi(b0), hi(b1), lo(b0), lo(b1)})
+__device__ __forceinline__ void hmma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint4& b) {
+    hmma16816(d, ah, b.x, b.y);
+    hmma16816(d, ah, b.z, b.w);
+    hmma16816(d, al, b.x, b.y);
+}
+
 template <class SH> struct Tc16Ctx;
 template <class SH>
 __device__ __forceinline__ void tc16_eval_fwd2(Tc16Ctx<SH>& c, const KParams& p, const float (&y)[2], float u, float (&f)[2], float& Hval);
@@ -369,6 +415,10 @@ struct Tc16Ctx {
     static constexpr bool kExpRLds = false;
 #endif
     __device__ __forceinline__ const float4* fields() const { return reinterpret_cast<const float4*>(phnn_smem + SH::OFF_SMALL); }
+    __device__ __forceinline__ const uint4* rfrag_fwd() const {
+        return reinterpret_cast<const uint4*>(phnn_smem + SH::OFF_SMALL + SH::NF * SH::NP * 16) + lane;
+    }
+    __device__ __forceinline__ const uint4* rfrag_bwd() const { return rfrag_fwd() + SH::RFRAG / 4; }
     __device__ __forceinline__ void gbar() const { __syncwarp(); }  // the co-owners of an instance are lanes of one quad
     __device__ __forceinline__ float own(float a, float b) const { return (cq & 2) ? b : a; }
     __device__ __forceinline__ float fromA(float v) const { return __shfl_sync(0xffffffffu, v, srcA); }
@@ -505,6 +555,41 @@ __device__ __forceinline__ void tc16_rfwd(const Tc16Ctx<SH>& c, int kb, const fl
     }
 }
 
+// The same on mma.sync fragments: the two groups K0, K0 + 1 of this lane's four are one K = 16 step whose operand A is
+// {r(A, K0), r(B, K0), r(A, K0+1), r(B, K0+1)} as FP16 hi/lo pairs (r times 2^9) -- exactly what the thread has just
+// computed; the 10 sums (padded to two n-tiles of 8) accumulate in SC: SC[4 nt + {0,1}] = sums 8 nt + 2 t + {0,1} of
+// instance A, SC[4 nt + {2,3}] of instance B, complete over all hidden units (no reduction over the quad).
+template <int K0, int K1, class SH>
+__device__ __forceinline__ void tc16_rfwd_mma(const Tc16Ctx<SH>& c, int kb, const float (&yA)[4], const float (&yB)[4], float (&SC)[2][4]) {
+    static_assert(K1 == K0 + 2 && (K0 & 1) == 0, "one K = 16 step");
+    const float4* F = c.fields();
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int k = K0; k < K1; ++k) {
+        const int P = tc16_pair(c, kb, k);
+        const float4 u01 = F[5 * SH::NP + P], u23 = F[6 * SH::NP + P];
+        const float2 br1 = zw(F[2 * SH::NP + P]);
+        split_f16x2(tanh16_scaled(pair_affine(u01, u23, yA, br1), 512.f), ah[2 * (k - K0)], al[2 * (k - K0)]);
+        split_f16x2(tanh16_scaled(pair_affine(u01, u23, yB, br1), 512.f), ah[2 * (k - K0) + 1], al[2 * (k - K0) + 1]);
+    }
+    const uint4* RF = c.rfrag_fwd() + (kb * 2 + (K0 >> 1)) * 2 * 32;
+    hmma3(SC[0], ah, al, RF[0]);
+    hmma3(SC[1], ah, al, RF[32]);
+    sched_fence();
+}
+// the 10 sums of the lane's own instance from the accumulator fragments of its quad
+template <class SH>
+__device__ __forceinline__ void tc16_rsums_own(const Tc16Ctx<SH>& c, const float (&SC)[2][4], float scale, float (&Sp)[12]) {
+    const int base = c.lane & ~3;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int nt = i >> 3, src = base + ((i & 7) >> 1);
+        const float a = __shfl_sync(0xffffffffu, SC[nt][i & 1], src);
+        const float b = __shfl_sync(0xffffffffu, SC[nt][2 + (i & 1)], src);
+        Sp[i] = c.own(a, b) * scale;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // f(y,u), H(y) for the tile's 128 instances (src/pHNN.py:52-100, src/pHNN_canonical.py:172-273)
 // ---------------------------------------------------------------------------------------
@@ -528,9 +613,20 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
     float zA[4], zB[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { zA[i] = c.fromA(z[i]); zB[i] = c.fromB(z[i]); }
-    float2 SpA[10], SpB[10];
+    float2 SpA[SH::RMMA ? 1 : 10], SpB[SH::RMMA ? 1 : 10];
+    float SC[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if constexpr (!SH::RMMA) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) { SpA[i] = make_float2(0.f, 0.f); SpB[i] = make_float2(0.f, 0.f); }
+        for (int i = 0; i < 10; ++i) { SpA[i] = make_float2(0.f, 0.f); SpB[i] = make_float2(0.f, 0.f); }
+    }
+    auto rfwd01 = [&](int kb) {
+        if constexpr (SH::RMMA) tc16_rfwd_mma<0, 2>(c, kb, zA, zB, SC);
+        else tc16_rfwd<0, 2>(c, kb, zA, zB, SpA, SpB);
+    };
+    auto rfwd23 = [&](int kb) {
+        if constexpr (SH::RMMA) tc16_rfwd_mma<2, 4>(c, kb, zA, zB, SC);
+        else tc16_rfwd<2, 4>(c, kb, zA, zB, SpA, SpB);
+    };
     // ---- phase A: a1 = tanh(W1 z + b1) -> operand A of product 1 (z2 = W2 a1), into the idle accumulator ----
     {
 #pragma unroll 1
@@ -553,12 +649,12 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
 #endif
             c.template put_block<true>(kb, a, p.s16[4]);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC16_RSKEW) tc16_rfwd<0, 2>(c, kb - PHNN_TC16_RSKEW, zA, zB, SpA, SpB);
+                if (kb >= PHNN_TC16_RSKEW) rfwd01(kb - PHNN_TC16_RSKEW);
             }
         }
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rfwd<0, 2>(c, kb, zA, zB, SpA, SpB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) rfwd01(kb);
         }
         c.end_feed();
     }
@@ -590,12 +686,12 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
 #endif
             c.template put_block<false>(kb, d, 1.0f);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC16_RSKEW) tc16_rfwd<2, 4>(c, kb - PHNN_TC16_RSKEW, zA, zB, SpA, SpB);
+                if (kb >= PHNN_TC16_RSKEW) rfwd23(kb - PHNN_TC16_RSKEW);
             }
         });
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rfwd<2, 4>(c, kb, zA, zB, SpA, SpB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) rfwd23(kb);
         }
         c.end_feed();
         Hown = c.quad_own_sum(HpA.x + HpA.y, HpB.x + HpB.y) * p.s16[5];
@@ -667,7 +763,9 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
         tc_fence_before();
     }
     float Sp[12];
-    if constexpr (SH::HAS_R) {
+    if constexpr (SH::RMMA) {
+        tc16_rsums_own(c, SC, p.s16[7], Sp);
+    } else if constexpr (SH::HAS_R) {
 #pragma unroll
         for (int i = 0; i < 10; ++i) Sp[i] = c.quad_own_sum(SpA[i].x + SpA[i].y, SpB[i].x + SpB[i].y);
     }
@@ -1013,6 +1111,31 @@ __device__ __forceinline__ void tc16_rback(const Tc16Ctx<SH>& c, int kb, const f
     }
 }
 
+// The same with the output-layer transpose on mma.sync fragments: operand A = the cotangents Rb of the two instances
+// (K = 10 sums padded to 16, FP16 hi/lo, scaled per instance), operand B = the weights of the 8 units of a group; the
+// accumulator fragment is this thread's pair of units for its two instances, in units of 2^q S_RW (inv = the inverse).
+template <int K0, int K1, class SH>
+__device__ __forceinline__ void tc16_rback_mma(const Tc16Ctx<SH>& c, int kb, const float (&yA)[4], const float (&yB)[4],
+                                               const uint32_t (&ah)[4], const uint32_t (&al)[4], float invA, float invB,
+                                               float2 (&XA)[4], float2 (&XB)[4]) {
+    const float4* F = c.fields();
+    const uint4* RB = c.rfrag_bwd() + kb * 4 * 32;
+#pragma unroll
+    for (int k = K0; k < K1; ++k) {
+        const int P = tc16_pair(c, kb, k);
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        hmma3(d, ah, al, RB[k * 32]);
+        const float4 u01 = F[5 * SH::NP + P], u23 = F[6 * SH::NP + P];
+        const float2 br1 = zw(F[2 * SH::NP + P]);
+        const float2 rA = tanh16(pair_affine(u01, u23, yA, br1));
+        const float2 rB = tanh16(pair_affine(u01, u23, yB, br1));
+        // inv (1 - r^2) = inv - (inv r) r
+        pair_scatter(u01, u23, mul2(make_float2(d[0], d[1]), fma2(mul2(rA, bc2(-invA)), rA, bc2(invA))), XA);
+        pair_scatter(u01, u23, mul2(make_float2(d[2], d[3]), fma2(mul2(rB, bc2(-invB)), rB, bc2(invB))), XB);
+        sched_fence();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // xbar = (df/dy)^T v, ubar = (df/du)^T v from the taped activations of the forward evaluation at the same stage state
 // and the Hessian-vector product of H_net.  Products: dz2 = W2 da1, dg1 = W2^T e2.
@@ -1097,15 +1220,52 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
 #pragma unroll
         for (int i = 0; i < 10; ++i) Rb[i] *= scr;
     }
-    float wA[4], wB[4], yA[4], yB[4], RbA[10], RbB[10];
+    float wA[4], wB[4], yA[4], yB[4], RbA[SH::RMMA ? 1 : 10], RbB[SH::RMMA ? 1 : 10];
+    uint32_t rah[4] = {0u, 0u, 0u, 0u}, ral[4] = {0u, 0u, 0u, 0u};  // Rb of the quad's two instances as mma.sync A fragments
+    float rinvA = 1.f, rinvB = 1.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { wA[i] = c.fromA(w[i]); wB[i] = c.fromB(w[i]); }
     if constexpr (SH::HAS_R) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { yA[i] = c.fromA(y[i]); yB[i] = c.fromB(y[i]); }
+        if constexpr (SH::RMMA) {
+            // one more exact power of two per instance puts max |Rb| in [2^11, 2^12) (FP16 hi + lo keeps 22 bits down
+            // to 2^-13 of that); the accumulator comes back times 2^q S_RW
+            float mr = 0.f;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) { RbA[i] = c.fromA(Rb[i]); RbB[i] = c.fromB(Rb[i]); }
+            for (int i = 0; i < 10; ++i) mr = fmaxf(mr, fabsf(Rb[i]));
+            int q = 138 - (int)((__float_as_uint(mr) >> 23) & 0xffu);
+            q = mr > 0.f ? min(max(q, -60), 60) : 0;
+            const float rs = __uint_as_float((uint32_t)(127 + q) << 23);
+            const float rinv = __uint_as_float((uint32_t)(127 - q - p.rexp16) << 23);
+            uint32_t wh[5], wl[5];
+#pragma unroll
+            for (int tt = 0; tt < 5; ++tt) split_f16x2(make_float2(Rb[2 * tt] * rs, Rb[2 * tt + 1] * rs), wh[tt], wl[tt]);
+#pragma unroll
+            for (int tt = 0; tt < 5; ++tt) {
+                const uint32_t xh = __shfl_sync(0xffffffffu, wh[tt], c.srcA), xl = __shfl_sync(0xffffffffu, wl[tt], c.srcA);
+                const uint32_t yh = __shfl_sync(0xffffffffu, wh[tt], c.srcB), yl = __shfl_sync(0xffffffffu, wl[tt], c.srcB);
+                if (tt < 4) {
+                    if (c.cq == tt) { rah[0] = xh; ral[0] = xl; rah[1] = yh; ral[1] = yl; }
+                } else if (c.cq == 0) {
+                    rah[2] = xh; ral[2] = xl; rah[3] = yh; ral[3] = yl;
+                }
+            }
+            rinvA = c.fromA(rinv);
+            rinvB = c.fromB(rinv);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { RbA[i] = c.fromA(Rb[i]); RbB[i] = c.fromB(Rb[i]); }
+        }
     }
+    auto rback01 = [&](int kb, float2 (&XA_)[4], float2 (&XB_)[4]) {
+        if constexpr (SH::RMMA) tc16_rback_mma<0, 2>(c, kb, yA, yB, rah, ral, rinvA, rinvB, XA_, XB_);
+        else tc16_rback<0, 2>(c, kb, yA, yB, RbA, RbB, XA_, XB_);
+    };
+    auto rback23 = [&](int kb, float2 (&XA_)[4], float2 (&XB_)[4]) {
+        if constexpr (SH::RMMA) tc16_rback_mma<2, 4>(c, kb, yA, yB, rah, ral, rinvA, rinvB, XA_, XB_);
+        else tc16_rback<2, 4>(c, kb, yA, yB, RbA, RbB, XA_, XB_);
+    };
     // xbar partials over my hidden units as (even, odd) pairs: X from the R_net chain and the dg1 half of xbar_H,
     // T the g1 half of xbar_H without its factor -2
     float2 XA[4], XB[4], TA[4], TB[4];
@@ -1142,7 +1302,7 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
             }
             c.template put_block<false>(kb, da, 1.0f);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC16_RSKEW) tc16_rback<0, 2>(c, kb - PHNN_TC16_RSKEW, yA, yB, RbA, RbB, XA, XB);
+                if (kb >= PHNN_TC16_RSKEW) rback01(kb - PHNN_TC16_RSKEW, XA, XB);
             }
         };
 #pragma unroll 1
@@ -1152,7 +1312,7 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
         }
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rback<0, 2>(c, kb, yA, yB, RbA, RbB, XA, XB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) rback01(kb, XA, XB);
         }
         c.end_feed();
     }
@@ -1177,12 +1337,12 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
             }
             c.template put_block<false>(kb, e2, 1.0f);
             if constexpr (SH::HAS_R) {
-                if (kb >= PHNN_TC16_RSKEW) tc16_rback<2, 4>(c, kb - PHNN_TC16_RSKEW, yA, yB, RbA, RbB, XA, XB);
+                if (kb >= PHNN_TC16_RSKEW) rback23(kb - PHNN_TC16_RSKEW, XA, XB);
             }
         });
         if constexpr (SH::HAS_R) {
 #pragma unroll
-            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) tc16_rback<2, 4>(c, kb, yA, yB, RbA, RbB, XA, XB);
+            for (int kb = NKB - PHNN_TC16_RSKEW; kb < NKB; ++kb) rback23(kb, XA, XB);
         }
         c.end_feed();
     }
