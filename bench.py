@@ -251,6 +251,8 @@ def main():
                     help="final exchange at N>1: NCCL all_gather, or the fused peer-store epilogue of the solve kernel")
     ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU time for the whole reference arm")
     ap.add_argument("--ref-batch", type=int, default=0, help="reference arm: instances per step (default: sized to --ref-budget)")
+    ap.add_argument("--tensor-pair", type=int, default=-1,
+                    help="1: solve jobs run as CTA pairs (tcgen05 cta_group::2, bit-identical results); default: the library's (0)")
     ap.add_argument("--tensor-mode", type=int, default=-1,
                     help="0 FP32-FMA kernel, 4 tcgen05 3 x FP16 hi/lo products with A in TMEM (default), 2 tcgen05 TF32 + BF16 "
                          "correction product, 3 tcgen05 3xTF32, 1 tcgen05 plain TF32")
@@ -307,6 +309,8 @@ def main():
     pk = PackedModel({k: torch.from_numpy(v) for k, v in sd.items()}, kind, device=dev)
     if args.tensor_mode >= 0:
         pk.set_option("tensor_mode", args.tensor_mode)
+    if args.tensor_pair >= 0:
+        pk.set_option("tensor_pair", args.tensor_pair)
     c = cost_for(kind)
     spec = CostSpec.make(4, 1, c["Q"], c["R"], None, c["u_min"], c["u_max"])
     mpc = BatchedMPC(pk, H, 0.02, spec, integrator=integ, lr=lr, iters=iters,
@@ -655,7 +659,7 @@ def main():
             "kernel_path": {5: "tcgen05-1xFP16-A-in-TMEM", 4: "tcgen05-3xFP16-A-in-TMEM", 3: "tcgen05-3xTF32", 2: "tcgen05-TF32+BF16corr", 1: "tcgen05-TF32"}[tmode] if uses_tc else "fp32-fma",
             "exchange": {"kind": gather_kind, "ms": gather_ms,
                          "note": "issued once per step, inside every timed step; `ms` is the exchange alone, warmed, median of 7"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "tensor_pair": int(pk.get_option("tensor_pair")),
             "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity, "fp16_mode5": alt,
             "rollout": rollout_metric, "step_ms": step_ms}
     print(json.dumps(line))
