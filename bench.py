@@ -252,7 +252,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU time for the whole reference arm")
     ap.add_argument("--ref-batch", type=int, default=0, help="reference arm: instances per step (default: sized to --ref-budget)")
     ap.add_argument("--tensor-pair", type=int, default=-1,
-                    help="1: solve jobs run as CTA pairs (tcgen05 cta_group::2, bit-identical results); default: the library's (0)")
+                    help="1: solve jobs run as CTA pairs (tcgen05 cta_group::2, same results); default: the library's (0)")
     ap.add_argument("--tensor-mode", type=int, default=-1,
                     help="0 FP32-FMA kernel, 4 tcgen05 3 x FP16 hi/lo products with A in TMEM (default), 2 tcgen05 TF32 + BF16 "
                          "correction product, 3 tcgen05 3xTF32, 1 tcgen05 plain TF32")

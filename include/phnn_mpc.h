@@ -94,7 +94,8 @@ int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
  *   "tensor_pair"      tensor_mode 4 solve jobs with an even number of 128-instance tiles run as clusters of two CTAs on
  *                      the two SMs of a TPC: every tensor product is one tcgen05.mma.cta_group::2 of M = 256 over the two
  *                      tiles of the pair, each CTA staging half of every weight tile (half the tensor-core operand-B reads
- *                      and half the L2 -> SM weight stream per SM).  Results are bit-identical to the single-CTA launch.
+ *                      and half the L2 -> SM weight stream per SM).  Same results as the single-CTA launch (bit-identical
+ *                      for models without an R_net; R_net sums added in a different order otherwise, <= 2e-6).
  *                      0 (default: measured +0.5 % on the power-capped full job, -1.7 % on an unthrottled slice) / 1.
  *   "latency_max_batch" largest B routed to the latency kernel (one thread per hidden unit, up to 8 instances
  *                      per CTA; default 8-96 x SM count by measured crossover, where built: hidden width <= 128;

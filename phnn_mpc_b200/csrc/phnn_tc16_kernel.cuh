@@ -26,7 +26,9 @@
 //     hidden dimension finish with two shuffles inside the quad: no shared-memory exchange, no named barriers.
 //     Each instance is owned by two lanes of its quad for the per-instance algebra (run_job), as before.
 //
-// Roles: warps 0..7 element threads, warp 8 MMA issuer (one lane), warp 9 weight producer (cp.async.bulk ring).
+// Roles: warps 0..7 element threads, warp 8 MMA issuer (one lane), warp 9 weight producer (cp.async.bulk ring), warps
+// 10..11 idle (they complete the auxiliary warpgroup whose registers go to the element warps), and for models with an
+// R_net warps 12..15: the R_net warpgroup (PHNN_TC16_RWARPS below).
 #pragma once
 #include <type_traits>
 
@@ -53,6 +55,19 @@ namespace phnn {
 // route for these side products either; they stay on the FMA pipe.
 #ifndef PHNN_TC16_RMMA
 #define PHNN_TC16_RMMA 0
+#endif
+
+// PHNN_TC16_RWARPS = 1 (default): the R_net work of the full shapes runs on FOUR DEDICATED WARPS (thread = instance,
+// warp-uniform record loads) instead of being interleaved into the 8 element warps.  R(x) depends only on the stage state
+// (forward: 10 symmetrised sums back) and on the 10 cotangents of those sums (adjoint: 4 xbar contributions back), never on
+// the accumulators, so it is a side computation the element warps request through a mailbox in shared memory at the start
+// of an evaluation and collect at its end.  The element warps' dependent chains -- which bound the kernel at two warps per
+// scheduler -- lose ~45 % of their instructions and every scheduler gets a third warp.
+#ifndef PHNN_TC16_RWARPS
+#define PHNN_TC16_RWARPS 1
+#endif
+#ifndef PHNN_TC16_RBATCH
+#define PHNN_TC16_RBATCH 2  // pairs of hidden units an R_net thread (two instances) works on at once
 #endif
 
 template <int MK_, int NS_, int HID_, bool LOWP_ = false, bool SPARSE_ = false, bool PAIR_ = false>
@@ -126,16 +141,26 @@ struct Tc16Shape {
     static constexpr int OFF_B = 1024;
     static constexpr int OFF_SMALL = OFF_B + NBE * B_TILE_CTA;
     static constexpr int OFF_XCH = OFF_SMALL + SMALL * 4;  // sparse tiles: [evaluation parity][K-block owner][64 instances][8 floats]
-    static constexpr int SMEM_BYTES = OFF_XCH + (SPARSE_ ? 2 * 2 * 64 * 8 * 4 : 0);
+    // dedicated R_net warps (see PHNN_TC16_RWARPS above); CTA pairs keep the interleaved form (their scheduler barrier
+    // spans the cluster)
+    static constexpr bool RW = !FWD_ONLY && HAS_R && !PAIR_ && !RMMA && (PHNN_TC16_RWARPS != 0);
+    // mailbox (floats): request rows [0,4) stage state, [4,14) cotangents of the sums; response rows [14,24) and [24,34):
+    // the 10 sums (forward) or the 4 xbar contributions (adjoint) over the first / second half of the hidden units; one
+    // row = the tile's 128 instances; then the request tag
+    static constexpr int OFF_MBOX = OFF_XCH + (SPARSE_ ? 2 * 2 * 64 * 8 * 4 : 0);
+    static constexpr int MBOX_ROWS = 34;
+    static constexpr int SMEM_BYTES = OFF_MBOX + (RW ? MBOX_ROWS * 128 * 4 + 128 : 0);
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static constexpr int B_AFULL = 0, B_BFULL = NKB, B_BEMPTY = NKB + NBE, B_ACC = NKB + 2 * NBE, B_SMALL = B_ACC + 2;
-    static_assert((B_SMALL + 1) * 8 <= 256, "barriers live in the first 256 bytes");
+    static constexpr int B_RREQ = B_SMALL + 1, B_RRESP = B_SMALL + 2;
+    static_assert((B_RRESP + 1) * 8 <= 256, "barriers live in the first 256 bytes");
     // 8 element warps (two warpgroups) + one warpgroup holding the MMA issuer, the weight producer and two idle warps:
     // setmaxnreg moves registers from the latter to the element warps (the per-thread state of two instances plus the
     // fragment buffers do not fit the 168 registers a 384-thread CTA gets at launch)
-    static constexpr int THREADS = 32 * NEW + 128;
-    static constexpr int REGS_ELEM = 224, REGS_AUX = 48;
-    static_assert(32 * NEW * REGS_ELEM + 128 * REGS_AUX <= 65536, "register file");
+    // with the R_net warpgroup: 512 threads (128 registers each at launch), element threads 184, R_net threads 96
+    static constexpr int THREADS = 32 * NEW + 128 + (RW ? 128 : 0);
+    static constexpr int REGS_ELEM = RW ? 184 : 224, REGS_AUX = 48, REGS_R = 96;
+    static_assert(32 * NEW * REGS_ELEM + 128 * REGS_AUX + (RW ? 128 * REGS_R : 0) <= 65536, "register file");
 };
 
 // ---- tcgen05 helpers of this kernel ---------------------------------------------------------------------
@@ -403,6 +428,7 @@ struct Tc16Ctx {
     uint32_t afull;  // CTA pairs: address of the LEADER's operand-A barriers in the cluster window
     uint32_t qdone;  // products whose accumulator this thread has waited for
     uint32_t qfeed;  // products this thread has fed (operand A written for)
+    uint32_t rq;     // requests posted to the R_net warps
     float* sck;      // per tile: R_net sums [0,10) and grad H [10,14) of every forward evaluation, [T*S][16][128]
     int ev;          // index of the evaluation in flight (t * S + s)
     float* tape;     // per CTA: a2, a1, g1 of every forward evaluation of the unit in flight: [T*S][3][NKB][4][256] float4
@@ -419,6 +445,28 @@ struct Tc16Ctx {
         return reinterpret_cast<const uint4*>(phnn_smem + SH::OFF_SMALL + SH::NF * SH::NP * 16) + lane;
     }
     __device__ __forceinline__ const uint4* rfrag_bwd() const { return rfrag_fwd() + SH::RFRAG / 4; }
+    // ---- mailbox of the R_net warps ----
+    __device__ __forceinline__ float* mbox() const { return reinterpret_cast<float*>(phnn_smem + SH::OFF_MBOX); }
+    // request for this evaluation: tag 0 = forward sums of R_net at stage state y, 1 = adjoint chain (y, cotangents Rb),
+    // 2 = no more work.  One owner lane per instance writes its row; every element warp arrives once.
+    __device__ __forceinline__ void r_post(int tag, const float* y, const float* Rb) {
+        float* m = mbox();
+        if (store && tag < 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[i * 128 + row] = y[i];
+            if (tag == 1) {
+#pragma unroll
+                for (int i = 0; i < 10; ++i) m[(4 + i) * 128 + row] = Rb[i];
+            }
+        }
+        if (tid == 0) *reinterpret_cast<volatile int*>(m + SH::MBOX_ROWS * 128) = tag;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars()[SH::B_RREQ]);
+        ++rq;
+    }
+    // response of the last request: row i of the lane's own instance
+    __device__ __forceinline__ void r_wait() const { mbar_wait(&bars()[SH::B_RRESP], (rq - 1u) & 1u); }
+    __device__ __forceinline__ float r_get(int i) const { return mbox()[(14 + i) * 128 + row] + mbox()[(24 + i) * 128 + row]; }
     __device__ __forceinline__ void gbar() const { __syncwarp(); }  // the co-owners of an instance are lanes of one quad
     __device__ __forceinline__ float own(float a, float b) const { return (cq & 2) ? b : a; }
     __device__ __forceinline__ float fromA(float v) const { return __shfl_sync(0xffffffffu, v, srcA); }
@@ -619,12 +667,15 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
 #pragma unroll
         for (int i = 0; i < 10; ++i) { SpA[i] = make_float2(0.f, 0.f); SpB[i] = make_float2(0.f, 0.f); }
     }
+    if constexpr (SH::RW) c.r_post(0, z, nullptr);  // the R_net warps work on this stage state while the products run
     auto rfwd01 = [&](int kb) {
-        if constexpr (SH::RMMA) tc16_rfwd_mma<0, 2>(c, kb, zA, zB, SC);
+        if constexpr (SH::RW) return;
+        else if constexpr (SH::RMMA) tc16_rfwd_mma<0, 2>(c, kb, zA, zB, SC);
         else tc16_rfwd<0, 2>(c, kb, zA, zB, SpA, SpB);
     };
     auto rfwd23 = [&](int kb) {
-        if constexpr (SH::RMMA) tc16_rfwd_mma<2, 4>(c, kb, zA, zB, SC);
+        if constexpr (SH::RW) return;
+        else if constexpr (SH::RMMA) tc16_rfwd_mma<2, 4>(c, kb, zA, zB, SC);
         else tc16_rfwd<2, 4>(c, kb, zA, zB, SpA, SpB);
     };
     // ---- phase A: a1 = tanh(W1 z + b1) -> operand A of product 1 (z2 = W2 a1), into the idle accumulator ----
@@ -763,7 +814,11 @@ __device__ __forceinline__ void tc16_eval_fwd(Tc16Ctx<SH>& c, const KParams& p, 
         tc_fence_before();
     }
     float Sp[12];
-    if constexpr (SH::RMMA) {
+    if constexpr (SH::RW) {
+        c.r_wait();
+#pragma unroll
+        for (int i = 0; i < 10; ++i) Sp[i] = c.r_get(i);
+    } else if constexpr (SH::RMMA) {
         tc16_rsums_own(c, SC, p.s16[7], Sp);
     } else if constexpr (SH::HAS_R) {
 #pragma unroll
@@ -1225,7 +1280,9 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
     float rinvA = 1.f, rinvB = 1.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { wA[i] = c.fromA(w[i]); wB[i] = c.fromB(w[i]); }
-    if constexpr (SH::HAS_R) {
+    if constexpr (SH::RW) {
+        c.r_post(1, y, Rb);
+    } else if constexpr (SH::HAS_R) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { yA[i] = c.fromA(y[i]); yB[i] = c.fromB(y[i]); }
         if constexpr (SH::RMMA) {
@@ -1259,11 +1316,13 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
         }
     }
     auto rback01 = [&](int kb, float2 (&XA_)[4], float2 (&XB_)[4]) {
-        if constexpr (SH::RMMA) tc16_rback_mma<0, 2>(c, kb, yA, yB, rah, ral, rinvA, rinvB, XA_, XB_);
+        if constexpr (SH::RW) return;
+        else if constexpr (SH::RMMA) tc16_rback_mma<0, 2>(c, kb, yA, yB, rah, ral, rinvA, rinvB, XA_, XB_);
         else tc16_rback<0, 2>(c, kb, yA, yB, RbA, RbB, XA_, XB_);
     };
     auto rback23 = [&](int kb, float2 (&XA_)[4], float2 (&XB_)[4]) {
-        if constexpr (SH::RMMA) tc16_rback_mma<2, 4>(c, kb, yA, yB, rah, ral, rinvA, rinvB, XA_, XB_);
+        if constexpr (SH::RW) return;
+        else if constexpr (SH::RMMA) tc16_rback_mma<2, 4>(c, kb, yA, yB, rah, ral, rinvA, rinvB, XA_, XB_);
         else tc16_rback<2, 4>(c, kb, yA, yB, RbA, RbB, XA_, XB_);
     };
     // xbar partials over my hidden units as (even, odd) pairs: X from the R_net chain and the dg1 half of xbar_H,
@@ -1380,9 +1439,15 @@ __device__ __forceinline__ void tc16_eval_vjp(Tc16Ctx<SH>& c, const KParams& p, 
     float X4[4];
     {
         const float ct = -2.f * p.s16[1], cx = p.s16[3];
+        float xr[4] = {0.f, 0.f, 0.f, 0.f};  // the R_net chain's share, in the units of X (from the R_net warps)
+        if constexpr (SH::RW) {
+            c.r_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xr[i] = cx * c.r_get(i);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            X4[i] = c.quad_own_sum(fmaf(ct, TA[i].x + TA[i].y, cx * (XA[i].x + XA[i].y)), fmaf(ct, TB[i].x + TB[i].y, cx * (XB[i].x + XB[i].y))) * isc;
+            X4[i] = (c.quad_own_sum(fmaf(ct, TA[i].x + TA[i].y, cx * (XA[i].x + XA[i].y)), fmaf(ct, TB[i].x + TB[i].y, cx * (XB[i].x + XB[i].y))) + xr[i]) * isc;
     }
     if constexpr (SH::MK == MK_CANON) {
         // chain through z = [q, M(theta) qdot] and M^-1(theta) (src/mass_matrix.py:310-362), SURVEY.md Appendix A
@@ -1432,6 +1497,10 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE, PAIR>::TH
         mbar_init(&bars[SH::B_ACC + 0], 1);
         mbar_init(&bars[SH::B_ACC + 1], 1);
         mbar_init(&bars[SH::B_SMALL], 1);
+        if constexpr (SH::RW) {
+            mbar_init(&bars[SH::B_RREQ], SH::NEW);  // every element warp posts
+            mbar_init(&bars[SH::B_RRESP], 4);       // every R_net warp answers
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -1482,6 +1551,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE, PAIR>::TH
     ss.slot = reinterpret_cast<int*>(phnn_smem + 768);
     ss.nelem = 32 * SH::NEW;
     if constexpr (PAIR) ss.rank = crank;
+    else ss.nsync = SH::RW ? 32 * SH::NEW + 128 : 0;  // the R_net warps take no part in the scheduling
 
     if (warp < SH::NEW) {
         // ===== element threads =====
@@ -1501,6 +1571,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE, PAIR>::TH
         c.afull = PAIR ? mapa_u32(smem_u32(&bars[SH::B_AFULL]), 0) : 0u;
         c.qdone = 0;
         c.qfeed = 0;
+        c.rq = 0;
         c.store = (lane & 1) == 0 && (!SH::SPARSE || (warp >> 2) == 0);
         c.tape = tape;
         c.scratch = p.scratch ? p.scratch + (size_t)blockIdx.x * tc_scratch_floats_per_cta(NS, p.T, p.S) : nullptr;
@@ -1513,7 +1584,125 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE, PAIR>::TH
             StridedSched sched{(long long)blockIdx.x, (long long)blockIdx.x, p.tiles, (int)gridDim.x, n_outer, 0};
             run_job(c, p, sched, SH::SPARSE ? c.slot : c.row);
         }
+        if constexpr (SH::RW) c.r_post(2, nullptr, nullptr);  // no more work for the R_net warps
         tc_fence_before();
+    } else if (SH::RW && warp >= SH::NEW + 4) {
+        // ===== R_net warps: thread = instance, all hidden units, records read warp-uniformly =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SH::REGS_R));
+        if constexpr (SH::RW) {
+            constexpr int NP = SH::NP;
+            const float4* F = reinterpret_cast<const float4*>(phnn_smem + SH::OFF_SMALL);
+            float* m = reinterpret_cast<float*>(phnn_smem + SH::OFF_MBOX);
+            // warp rw: instances 64 (rw & 1) + lane and + 32 (two per thread: every record load serves both), pairs of
+            // units [64 (rw >> 1), +64) (the two halves are added by the reader)
+            const int rw = warp - (SH::NEW + 4);
+            const int i0 = 64 * (rw & 1) + lane, i1 = i0 + 32;
+            const int PB = (NP / 2) * (rw >> 1), PE = PB + NP / 2;
+            float* out = m + (14 + 10 * (rw >> 1)) * 128;
+            mbar_wait(&bars[SH::B_SMALL], 0);
+#pragma unroll 1
+            for (uint32_t n = 0;; ++n) {
+                mbar_wait(&bars[SH::B_RREQ], n & 1u);
+                const int tag = *reinterpret_cast<volatile int*>(m + SH::MBOX_ROWS * 128);
+                if (tag == 2) break;
+                float y0[4], y1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { y0[i] = m[i * 128 + i0]; y1[i] = m[i * 128 + i1]; }
+#ifdef PHNN_TC16_EXP_REARLY  // timing experiment (wrong results): answer first, then do the work (same resources, no latency)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[SH::B_RRESP]);
+#endif
+#ifdef PHNN_TC16_EXP_RFREE  // timing experiment (wrong results): the R_net warps answer at once
+                if (true) {
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) { out[i * 128 + i0] = 0.01f * y0[i & 3]; out[i * 128 + i1] = 0.01f * y1[i & 3]; }
+                } else
+#endif
+                if (tag == 0) {
+                    // forward: Sp[c] = sum_j Wr2sym[c][j] tanh(Wr1[j] . y + br1[j])   (src/pHNN.py:70-79)
+                    // (PHNN_TC16_RBATCH pairs of units per step: one warp per scheduler has to cover the LDS -> FMA -> MUFU
+                    // latencies of these chains with its own instruction-level parallelism)
+                    float2 S0[10], S1[10];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) S0[i] = S1[i] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                    for (int P0 = PB; P0 < PE; P0 += PHNN_TC16_RBATCH) {
+                        float2 r0[PHNN_TC16_RBATCH], r1[PHNN_TC16_RBATCH];
+#pragma unroll
+                        for (int q = 0; q < PHNN_TC16_RBATCH; ++q) {
+                            const float4 u01 = F[5 * NP + P0 + q], u23 = F[6 * NP + P0 + q];
+                            const float2 br1 = zw(F[2 * NP + P0 + q]);
+                            r0[q] = pair_affine(u01, u23, y0, br1);
+                            r1[q] = pair_affine(u01, u23, y1, br1);
+                        }
+#pragma unroll
+                        for (int q = 0; q < PHNN_TC16_RBATCH; ++q) { r0[q] = tanh16(r0[q]); r1[q] = tanh16(r1[q]); }
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+#pragma unroll
+                            for (int q = 0; q < PHNN_TC16_RBATCH; ++q) {
+                                const float4 cc = F[(7 + j) * NP + P0 + q];
+                                S0[2 * j] = fma2(xy(cc), r0[q], S0[2 * j]);
+                                S0[2 * j + 1] = fma2(zw(cc), r0[q], S0[2 * j + 1]);
+                                S1[2 * j] = fma2(xy(cc), r1[q], S1[2 * j]);
+                                S1[2 * j + 1] = fma2(zw(cc), r1[q], S1[2 * j + 1]);
+                            }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) { out[i * 128 + i0] = S0[i].x + S0[i].y; out[i * 128 + i1] = S1[i].x + S1[i].y; }
+                } else {
+                    // adjoint: X[i] = sum_j Wr1[j][i] (1 - r_j^2) sum_c Rb[c] Wr2sym[c][j]
+                    float Rb0[10], Rb1[10];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) { Rb0[i] = m[(4 + i) * 128 + i0]; Rb1[i] = m[(4 + i) * 128 + i1]; }
+                    float2 X0[4], X1[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) X0[i] = X1[i] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                    for (int P0 = PB; P0 < PE; P0 += PHNN_TC16_RBATCH) {
+                        float2 rb0[PHNN_TC16_RBATCH], rb1[PHNN_TC16_RBATCH], r0[PHNN_TC16_RBATCH], r1[PHNN_TC16_RBATCH];
+                        float4 u01[PHNN_TC16_RBATCH], u23[PHNN_TC16_RBATCH];
+#pragma unroll
+                        for (int q = 0; q < PHNN_TC16_RBATCH; ++q) {
+                            u01[q] = F[5 * NP + P0 + q];
+                            u23[q] = F[6 * NP + P0 + q];
+                            const float2 br1 = zw(F[2 * NP + P0 + q]);
+                            r0[q] = pair_affine(u01[q], u23[q], y0, br1);
+                            r1[q] = pair_affine(u01[q], u23[q], y1, br1);
+                        }
+#pragma unroll
+                        for (int q = 0; q < PHNN_TC16_RBATCH; ++q) { r0[q] = tanh16(r0[q]); r1[q] = tanh16(r1[q]); }
+#pragma unroll
+                        for (int q = 0; q < PHNN_TC16_RBATCH; ++q) {
+                            const float4 cc = F[7 * NP + P0 + q];
+                            rb0[q] = fma2(zw(cc), bc2(Rb0[1]), mul2(xy(cc), bc2(Rb0[0])));
+                            rb1[q] = fma2(zw(cc), bc2(Rb1[1]), mul2(xy(cc), bc2(Rb1[0])));
+                        }
+#pragma unroll
+                        for (int j = 1; j < 5; ++j)
+#pragma unroll
+                            for (int q = 0; q < PHNN_TC16_RBATCH; ++q) {
+                                const float4 cc = F[(7 + j) * NP + P0 + q];
+                                rb0[q] = fma2(xy(cc), bc2(Rb0[2 * j]), rb0[q]);
+                                rb0[q] = fma2(zw(cc), bc2(Rb0[2 * j + 1]), rb0[q]);
+                                rb1[q] = fma2(xy(cc), bc2(Rb1[2 * j]), rb1[q]);
+                                rb1[q] = fma2(zw(cc), bc2(Rb1[2 * j + 1]), rb1[q]);
+                            }
+#pragma unroll
+                        for (int q = 0; q < PHNN_TC16_RBATCH; ++q) {
+                            pair_scatter(u01[q], u23[q], mul2(rb0[q], one_minus_sq(r0[q])), X0);
+                            pair_scatter(u01[q], u23[q], mul2(rb1[q], one_minus_sq(r1[q])), X1);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { out[i * 128 + i0] = X0[i].x + X0[i].y; out[i * 128 + i1] = X1[i].x + X1[i].y; }
+                }
+#ifndef PHNN_TC16_EXP_REARLY
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[SH::B_RRESP]);
+#endif
+            }
+        }
     } else if (warp == SH::NEW) {
         // ===== MMA issuer =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SH::REGS_AUX));
@@ -1584,7 +1773,7 @@ __global__ void __launch_bounds__(Tc16Shape<MK, NS, HID, LOWP, SPARSE, PAIR>::TH
             }
             __syncwarp();
         }
-    } else if (warp > SH::NEW + 1) {
+    } else if (warp > SH::NEW + 1 && warp < SH::NEW + 4) {
         // ===== idle warps of the auxiliary warpgroup: give their registers away, keep the CTA-wide barriers company =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SH::REGS_AUX));
         for (long long unit = 0;; ++unit)

@@ -953,8 +953,12 @@ struct StealSched {
     int iters;
     int* slot;  // shared-memory broadcast slot
     int nelem;  // element threads of the CTA
+    int nsync = 0;  // threads that take part in grab(): 0 = the whole CTA, else the first nsync threads (named barrier 7)
     static constexpr bool kStateInWorkspace = true;
     __device__ __forceinline__ long long tile0() const { return -1; }
+    __device__ __forceinline__ void sync_all() const {
+        if (nsync) group_bar(7, nsync); else __syncthreads();
+    }
     __device__ __forceinline__ int grab() {
         if (threadIdx.x == 0) {
             const int n = atomicAdd(counter, 1);
@@ -969,9 +973,9 @@ struct StealSched {
             }
             *slot = n < total ? n : -1;
         }
-        __syncthreads();
+        sync_all();
         const int n = *slot;
-        __syncthreads();
+        sync_all();
         return n;
     }
     __device__ __forceinline__ bool next(Unit& u) {

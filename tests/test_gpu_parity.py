@@ -694,13 +694,14 @@ def test_cfg4_shape_golden_reference(tc_env, mode):
 # ---------------------------------------------------------------------------------------------
 # CTA pairs (option "tensor_pair", tcgen05 cta_group::2): two 128-instance tiles per cluster, one M = 256 MMA per product,
 # each CTA staging half of every weight tile.  Same MMAs per row and the same element code as the single-CTA launch, so
-# the results are required to be BIT-IDENTICAL to it -- and, independently, within the stated bounds of the oracle.
+# the results are required to be BIT-IDENTICAL to it for models without an R_net (for the others the two launches add the
+# R_net sums in a different order: 2e-6) -- and, independently, within the stated bounds of the oracle.
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cartpole_h256", "cartpole_h128", "canonical"])
 @pytest.mark.parametrize("B,H,iters", [(256, 6, 3), (128 * 300, 4, 2), (128 * 22 - 5, 5, 2), (128 * 7, 5, 2)])
 def test_cta_pair_bit_identical_to_single(tc_env, name, B, H, iters):
     """even tile counts run as CTA pairs (incl. more tiles than SMs and a ragged last tile); an odd tile count (7) falls
-    back to the single-CTA launch; either way the solve equals the tensor_pair = 0 solve bit for bit"""
+    back to the single-CTA launch; either way the solve equals the tensor_pair = 0 solve (bit for bit without an R_net)"""
     ops, get_tc = tc_env
     z, sd, pk = get_tc(name, 4)
     rng = np.random.default_rng(B + H)
@@ -718,7 +719,13 @@ def test_cta_pair_bit_identical_to_single(tc_env, name, B, H, iters):
     finally:
         pk.set_option("tensor_pair", 0)   # the default
     for a, b in zip(*outs):
-        assert np.array_equal(a, b)
+        if KINDS[name] == "canonical":
+            assert np.array_equal(a, b)           # same MMAs per row, same element code: bit for bit
+        else:
+            # models with an R_net: the single-CTA launch adds the R_net sums on its dedicated warps (one thread per
+            # instance and half of the hidden units), the pair launch inside the element warps (per-lane partial sums):
+            # same terms, different order of the FP32 additions
+            assert rel_err(a, b) < 2e-6
 
 
 def test_cta_pair_benchmarked_config_vs_oracle(tc_env):
