@@ -98,7 +98,7 @@ int phnn_pack_dims(const phnn_pack *pack, int *kind, int *n, int *m, int *h);
  *                      for models without an R_net; R_net sums added in a different order otherwise, <= 2e-6).
  *                      0 (default: measured +0.5 % on the power-capped full job, -1.7 % on an unthrottled slice) / 1.
  *   "latency_max_batch" largest B routed to the latency kernel (one thread per hidden unit, up to 8 instances
- *                      per CTA; default 8-96 x SM count by measured crossover, where built: hidden width <= 128;
+ *                      per CTA; default 4-96 x SM count by measured crossover, where built: hidden width <= 128;
  *                      0 disables it).                                                                                   */
 int phnn_pack_set_option(phnn_pack *pack, const char *key, long value);
 long phnn_pack_get_option(const phnn_pack *pack, const char *key);

@@ -609,8 +609,9 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
     pk->small_floats = small.size();
     // crossover measured on B200 (tools/gpu_crossover.py) with up to 8 (h = 64) / 4 (h = 128) instances per CTA: the
     // latency kernel wins up to ~100 instances per SM at h = 64, ~34 per SM at h = 128 against the FP32-FMA kernel and
-    // ~8 per SM against the tcgen05 kernel
-    pk->lat_max_batch = !has_lat_shape(mk, n, h) ? 0 : (h <= 64 ? 96L : (pk->d_wtc ? 8L : 32L)) * pk->num_sms;
+    // up to ONE WAVE of its 4-instance CTAs against the second-generation tcgen05 kernel (h = 128, 50 Euler iterations
+    // of H = 10: 5.7 ms at 592 instances, 11.0 ms from 593 on, tcgen05 7.7 ms for any batch up to one tile per SM)
+    pk->lat_max_batch = !has_lat_shape(mk, n, h) ? 0 : (h <= 64 ? 96L : (pk->d_wtc ? 4L : 32L)) * pk->num_sms;
     KParams& P = pk->base;
     P.wsmall = pk->d_small;
     P.wbig = pk->d_big;

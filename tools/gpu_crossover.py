@@ -16,7 +16,7 @@ for name, kind, H, iters, lr in (("cartpole_h128", "phnn", 20, 30, 0.015), ("can
     z, sd = load_golden(name)
     n = 2 if name == "pendulum" else 4
     spec = CostSpec.make(n, 1, [10.0, 200.0, 1.0, 10.0][:n], [0.01], None, -15.0, 15.0)
-    for B in (148, 296, 592, 1184, 2368, 4736, 9472):
+    for B in [int(b) for b in (os.environ.get("SWEEP") or "148,296,592,1184,2368,4736,9472").split(",")]:
         x0 = (torch.rand(B, n) * 0.2 - 0.1).cuda()
         res = []
         for route in ("lat", "ffma", "tc"):
