@@ -371,6 +371,35 @@ def gen_cfg4_shape():
     print("cfg4_shape done; cost[0] first/last =", res["hist"][0, 0], res["hist"][-1, 0])
 
 
+def gen_cfg5_shape():
+    """BASELINE cfg5 horizons at a reference-runnable size: the cfg4/cfg5 model (cartpole_h256.npz weights), the first 16
+    of the benchmark's own instances, H = 100 and H = 200, RK4, 4 Adam iterations, cold start (the long horizons were
+    pinned only through the oracle before).  About a minute of reference CPU time."""
+    z = np.load(os.path.join(HERE, "cartpole_h256.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model = pHNN(wide_cfg(256))
+    model.load_state_dict(sd)
+    model.eval()
+    cfg = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    mpc = cfg["mpc"]
+    g = torch.Generator().manual_seed(7)
+    B, iters = 16, 4
+    x0 = ((torch.rand(65536, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])).float()[:B]
+    Q = torch.diag(torch.tensor(mpc["Q_diag"]))
+    R = torch.tensor([[mpc["R_diag"][0]]])
+    xt = torch.tensor(mpc["x_target"])
+    dt = cfg["cartpole"]["dt"]
+    out = {"x0": x0.numpy(), "iters": np.int32(iters), "dt": np.float32(dt), "lr": np.float32(mpc["learning_rate"]),
+           "Q": Q.numpy(), "R": R.numpy(), "xt": xt.numpy(), "bounds": np.array([mpc["u_min"], mpc["u_max"]], np.float32)}
+    for Hh in (100, 200):
+        res = composition_solve(model, x0, torch.zeros(B, Hh, 1), dt, "rk4", Q, R, xt, mpc["u_min"], mpc["u_max"],
+                                mpc["learning_rate"], iters, "last")
+        for k, val in res.items():
+            out["h%d_%s" % (Hh, k)] = val
+        print("cfg5_shape H=%d done; cost[0] first/last =" % Hh, res["hist"][0, 0], res["hist"][-1, 0])
+    np.savez(os.path.join(HERE, "cfg5_shape.npz"), **out)
+
+
 def gen_train():
     """Weight gradients of the reference's own training losses, by autograd:
     scripts/train_cartpole_phnn.py:108-178 (pHNN: Euler unroll, position MSE + angle cosine + velocity MSE; the energy
@@ -448,7 +477,7 @@ def gen_train():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "train"]
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train"]
     if "pendulum" in which:
         gen_pendulum()
     if "h128" in which:
@@ -461,5 +490,7 @@ if __name__ == "__main__":
         gen_closed_loop()
     if "cfg4_shape" in which:
         gen_cfg4_shape()
+    if "cfg5_shape" in which:
+        gen_cfg5_shape()
     if "train" in which:
         gen_train()

@@ -752,3 +752,26 @@ def test_cta_pair_benchmarked_config_vs_oracle(tc_env):
     assert rel_err(hist.cpu().numpy(), histo) < HORIZON_TOL
     assert rel_err(best.cpu().numpy(), besto) < HORIZON_TOL
     assert np.abs(U.cpu().numpy() - Uo).max() < 0.02 * lr + 1e-5
+
+
+@pytest.mark.parametrize("mode", [4, 2])
+@pytest.mark.parametrize("H", [100, 200])
+def test_cfg5_shape_golden_reference(tc_env, H, mode):
+    """BASELINE cfg5 horizons against the fixture recorded from the REFERENCE ITSELF (one hop, no oracle):
+    tests/golden/cfg5_shape.npz = make_golden.gen_cfg5_shape (cfg4 weights, bench.py's first 16 instances, RK4, 4 Adam
+    iterations; reference PyTorch autograd + torch.optim.Adam).  Stated long-horizon bounds of DESIGN.md section 2."""
+    ops, get_tc = tc_env
+    _, sd, pk = get_tc("cartpole_h256", mode)
+    z, _ = load_golden("cfg5_shape")
+    B, iters, lr = z["x0"].shape[0], int(z["iters"]), float(z["lr"])
+    assert np.array_equal(_bench_inputs(B).numpy(), z["x0"])
+    U0 = np.zeros((B, H, 1), np.float32)
+    _, _, ca = _cfg4_cost()
+    p = "h%d_" % H
+    tol = HORIZON_TOL * H / 50.0
+    U, hist, best = ops.mpc_solve(pk.handle, cu(z["x0"]), cu(U0), float(z["dt"]), 1, *ca, lr, 0.9, 0.999, 1e-8, iters, 0, True)
+    assert rel_err(hist.cpu().numpy(), z[p + "hist"]) < tol
+    assert rel_err(best.cpu().numpy(), z[p + "best"]) < tol
+    assert np.abs(U.cpu().numpy() - z[p + "U_last"]).max() < 0.05 * lr
+    _, g0, _ = ops.cost_grad(pk.handle, cu(z["x0"]), cu(U0), float(z["dt"]), 1, *ca, True, False)
+    assert rel_err(g0.cpu().numpy(), z[p + "grad0"]) < 5 * tol

@@ -136,3 +136,26 @@ def test_oracle_cfg4_shape_vs_reference():
     assert np.abs(U - z["rk4_U_last"]).max() < 0.02 * float(z["lr"]) + 1e-5
     _, g0 = M.cost_grad(C, z["x0"], U0, float(z["dt"]), "rk4")
     assert rel_err(g0, z["rk4_grad0"]) < 1e-4
+
+
+@pytest.mark.parametrize("H", [100, 200])
+def test_oracle_cfg5_shape_vs_reference(H):
+    """BASELINE cfg5 horizons (cfg4 weights, bench.py's first 16 instances, H = 100 / 200, RK4, 4 Adam iterations) recorded
+    from the reference itself (make_golden.gen_cfg5_shape).  Long horizons amplify FP32 rounding (the cart-pole model is
+    unstable): stated bounds cost 1e-4 * H/50, dJ/dU 5e-4 * H/50, controls 0.05 * lr."""
+    from oracle.phnn_oracle import OracleModel, set_threads
+    import os
+    z, _ = load_golden("cfg5_shape")
+    _, sd = load_golden("cartpole_h256")
+    set_threads(os.cpu_count() or 1)
+    M = OracleModel(sd, "phnn")
+    C = M.cost_struct(z["Q"], z["R"], z["xt"], float(z["bounds"][0]), float(z["bounds"][1]))
+    B, iters = z["x0"].shape[0], int(z["iters"])
+    U0 = np.zeros((B, H, 1), np.float32)
+    p = "h%d_" % H
+    tol = 1e-4 * H / 50.0
+    U, hist, best = M.mpc_solve(C, z["x0"], U0, float(z["dt"]), "rk4", lr=float(z["lr"]), iters=iters)
+    assert rel_err(hist, z[p + "hist"]) < tol and rel_err(best, z[p + "best"]) < tol
+    assert np.abs(U - z[p + "U_last"]).max() < 0.05 * float(z["lr"])
+    _, g0 = M.cost_grad(C, z["x0"], U0, float(z["dt"]), "rk4")
+    assert rel_err(g0, z[p + "grad0"]) < 5 * tol
