@@ -50,6 +50,9 @@ typedef struct phnn_model_desc {
     const float *G;                            /* [n,m] G_fixed (kind 0) / G (kind 1)            */
     float mass_a, mass_b, mass_c;              /* kind 1: exp(log_a)+1e-3, b, exp(log_c)+1e-3    */
     const float *r_diag;                       /* kind 1: softplus(R_diag_raw)+1e-4, [n]         */
+    int mass_const;                            /* kind 1: 1 = constant mass matrix M = [[a,b],[b,c]] = L L^T
+                                                  (MassMatrixNetwork 'constant', src/mass_matrix.py:130-147,190-200:
+                                                  no cos(theta), exact inverse); 0 = cart-pole M(theta)              */
 } phnn_model_desc;
 
 /* Horizon cost of the controllers (src/mpc_controller.py:75-114,

@@ -52,6 +52,7 @@ typedef struct {
     const REAL *G;       /* [n,m] fixed input matrix                                          */
     REAL ma, mb, mc;     /* kind 1: a = exp(log_a)+1e-3, b, c = exp(log_c)+1e-3               */
     const REAL *rdiag;   /* kind 1: softplus(R_diag_raw)+1e-4, [n]                            */
+    int mconst;          /* kind 1: 1 = constant mass matrix [[a,b],[b,c]] (MassMatrixNetwork 'constant') */
 } FN(oracle_model);
 
 typedef struct {
@@ -205,7 +206,7 @@ static void FN(f_eval)(const FN(oracle_model) * M, const REAL *x, const REAL *u,
         /* canonical, cart-pole mass matrix, q_dim = 2 (src/pHNN_canonical.py:172-273)        */
         const REAL a = M->ma, b = M->mb, cc = M->mc;
         const REAL th = x[1];
-        const REAL beta = b * (REAL)cos((double)th);
+        const REAL beta = M->mconst ? b : b * (REAL)cos((double)th);   /* constant M: mass_matrix.py:130-147 */
         REAL z[4];
         z[0] = x[0];
         z[1] = x[1];
@@ -223,9 +224,10 @@ static void FN(f_eval)(const FN(oracle_model) * M, const REAL *x, const REAL *u,
             for (int j = 0; j < m; ++j) gu += M->G[r * m + j] * u[j];
             dz[r] = s + gu;
         }
-        const REAL D = a * cc - beta * beta + (REAL)1e-6;        /* mass_matrix.py:350-353     */
+        /* cart-pole: mass_matrix.py:350-353; constant M: exact inverse, mass_matrix.py:190-200 */
+        const REAL D = a * cc - beta * beta + (M->mconst ? (REAL)0 : (REAL)1e-6);
         const REAL n11 = cc / D, n12 = -beta / D, n22 = a / D;
-        c->beta = beta; c->D = D; c->sth = (REAL)sin((double)th);
+        c->beta = beta; c->D = D; c->sth = M->mconst ? (REAL)0 : (REAL)sin((double)th);
         c->p[0] = z[2]; c->p[1] = z[3];
         c->pdot[0] = dz[2]; c->pdot[1] = dz[3];
         for (int e = 0; e < n * m; ++e) c->G[e] = M->G[e];

@@ -22,7 +22,7 @@ class ModelDesc(ctypes.Structure):
                 ("Wg1", _fp), ("bg1", _fp), ("Wg2", _fp), ("bg2", _fp),
                 ("J", _fp), ("G", _fp),
                 ("mass_a", ctypes.c_float), ("mass_b", ctypes.c_float), ("mass_c", ctypes.c_float),
-                ("r_diag", _fp)]
+                ("r_diag", _fp), ("mass_const", ctypes.c_int)]
 
 
 class CostDesc(ctypes.Structure):

@@ -639,6 +639,7 @@ extern "C" int phnn_pack_create(const phnn_model_desc* d, int device, phnn_pack*
         for (int a = 0; a < n; ++a) P.bg2[a] = d->bg2[a];
     if (mk == MK_CANON) {
         P.ma = d->mass_a; P.mb = d->mass_b; P.mc = d->mass_c;
+        P.mconst = d->mass_const != 0;
         for (int a = 0; a < n; ++a) P.rdiag[a] = d->r_diag[a];
     }
     *out = pk;

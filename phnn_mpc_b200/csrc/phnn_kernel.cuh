@@ -100,6 +100,7 @@ struct KParams {
     float Jm[16];  // MK 0/1: J - J^T ; MK 2: the canonical J buffer
     float Gv[4];
     float b3, ma, mb, mc;
+    int mconst;  // canonical: 1 = constant mass matrix [[ma, mb], [mb, mc]] (no cos(theta), exact inverse)
     float br2[16];
     float bsym[12];  // tcgen05 path: (br2[ab] + br2[ba])/2 packed 00 01 02 03 11 12 13 22 23 33
     float bg2[4];
@@ -416,10 +417,16 @@ struct Canon {
 __device__ __forceinline__ Canon canon_of(const KParams& p, float theta) {
     Canon q;
     float s, cth;
-    sincosf(theta, &s, &cth);
+    if (p.mconst) {
+        // constant mass matrix (MassMatrixNetwork 'constant', src/mass_matrix.py:130-147): M = [[a, b], [b, c]], exact inverse
+        s = 0.f;
+        cth = 1.f;
+    } else {
+        sincosf(theta, &s, &cth);
+    }
     q.sth = s;
     q.beta = p.mb * cth;
-    q.D = p.ma * p.mc - q.beta * q.beta + 1e-6f;
+    q.D = p.ma * p.mc - q.beta * q.beta + (p.mconst ? 0.f : 1e-6f);
     q.n11 = p.mc / q.D;
     q.n12 = -q.beta / q.D;
     q.n22 = p.ma / q.D;

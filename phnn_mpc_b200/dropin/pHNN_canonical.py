@@ -6,12 +6,12 @@ import yaml
 
 try:
     from .NN import MLP
-    from .mass_matrix import CartPoleMassMatrix
+    from .mass_matrix import CartPoleMassMatrix, MassMatrixNetwork
     from .coordinate_transforms import kinematic_to_canonical, momentum_to_velocity, split_state
     from .pHNN import _mlp_from_config, run_forward_op, _flatten_rows
 except ImportError:
     from NN import MLP  # noqa: F401
-    from mass_matrix import CartPoleMassMatrix
+    from mass_matrix import CartPoleMassMatrix, MassMatrixNetwork
     from coordinate_transforms import kinematic_to_canonical, momentum_to_velocity, split_state
     from pHNN import _mlp_from_config, run_forward_op, _flatten_rows
 
@@ -25,11 +25,17 @@ class pHNN_Canonical(nn.Module):
         self.input_dim = model_cfg["input_dim"]
         self.q_dim = self.state_dim // 2
         mm = model_cfg.get("mass_matrix", {})
-        if mm.get("type", "cartpole") != "cartpole":
-            raise NotImplementedError("only the cart-pole mass matrix is implemented (the one every shipped "
-                                      "config uses); MassMatrixNetwork variants are out of scope")
-        self.M_net = CartPoleMassMatrix(init_a=mm.get("init_a", 1.0), init_b=mm.get("init_b", 0.1),
-                                        init_c=mm.get("init_c", 1.0))
+        if mm.get("type", "cartpole") == "cartpole":
+            self.M_net = CartPoleMassMatrix(init_a=mm.get("init_a", 1.0), init_b=mm.get("init_b", 0.1),
+                                            init_c=mm.get("init_c", 1.0))
+        else:
+            # src/pHNN_canonical.py:79-86: any other type is a MassMatrixNetwork; 'constant' is built for the CUDA path,
+            # the configuration-dependent types ('diagonal', 'full') raise NotImplementedError
+            if self.q_dim != 2:
+                raise NotImplementedError("the CUDA kernels are built for q_dim = 2")
+            self.M_net = MassMatrixNetwork(q_dim=self.q_dim, mass_type=mm["type"],
+                                           hidden_sizes=mm.get("hidden_sizes", [64, 64]),
+                                           init_scale=mm.get("init_scale", 1.0))
         self.H_net = _mlp_from_config(model_cfg["H_mlp"], self.state_dim, 1)
         if not self.H_net.kernel_compatible():
             raise NotImplementedError("CUDA kernels cover Tanh MLPs with bias and without LayerNorm/Dropout")

@@ -24,6 +24,18 @@ def infer_kind(sd):
     return "canonical" if "R_diag_raw" in sd else "phnn"
 
 
+def constant_mass_abc(L_tril):
+    """(a, b, c) of the constant mass matrix M = L L^T = [[a, b], [b, c]] of MassMatrixNetwork(mass_type='constant')
+    (src/mass_matrix.py:130-147): L = tril(L_tril) with softplus(diag) + 1e-3 on the diagonal, float32 arithmetic."""
+    L = torch.tril(torch.as_tensor(L_tril).detach().float().cpu())
+    if tuple(L.shape) != (2, 2):
+        raise NotImplementedError("constant mass matrix: q_dim = 2 (the cart-pole case the kernels are built for)")
+    l00 = torch.nn.functional.softplus(L[0, 0]) + 1e-3
+    l11 = torch.nn.functional.softplus(L[1, 1]) + 1e-3
+    l10 = L[1, 0]
+    return float(l00 * l00), float(l10 * l00), float(l10 * l10 + l11 * l11)
+
+
 class PackedModel:
     """Owns one phnn_pack handle (immutable device copy of the weights)."""
 
@@ -81,11 +93,19 @@ class PackedModel:
             d.m = int(sd["G"].shape[1])
             d.G = ptr("G")
             # src/mass_matrix.py:283-285 (float32 arithmetic) and src/pHNN_canonical.py:162
-            la = torch.as_tensor(sd["M_net.log_a"]).detach().float()
-            lc = torch.as_tensor(sd["M_net.log_c"]).detach().float()
-            d.mass_a = float(torch.exp(la) + 1e-3)
-            d.mass_b = float(torch.as_tensor(sd["M_net.b"]).detach().float())
-            d.mass_c = float(torch.exp(lc) + 1e-3)
+            if "M_net.L_tril" in sd:
+                # MassMatrixNetwork 'constant' (src/mass_matrix.py:130-147): M = L L^T, diag(L) = softplus(.) + 1e-3
+                d.mass_a, d.mass_b, d.mass_c = constant_mass_abc(sd["M_net.L_tril"])
+                d.mass_const = 1
+            elif any(k.startswith("M_net.mlp.") for k in sd):
+                raise NotImplementedError("configuration-dependent MassMatrixNetwork ('diagonal' / 'full') is not built; "
+                                          "the kernels cover the cart-pole and the constant mass matrix")
+            else:
+                la = torch.as_tensor(sd["M_net.log_a"]).detach().float()
+                lc = torch.as_tensor(sd["M_net.log_c"]).detach().float()
+                d.mass_a = float(torch.exp(la) + 1e-3)
+                d.mass_b = float(torch.as_tensor(sd["M_net.b"]).detach().float())
+                d.mass_c = float(torch.exp(lc) + 1e-3)
             rd = torch.nn.functional.softplus(torch.as_tensor(sd["R_diag_raw"]).detach().float()) + 1e-4
             sd["__r_diag"] = rd
             d.r_diag = ptr("__r_diag")

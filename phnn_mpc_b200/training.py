@@ -75,6 +75,11 @@ class _TrainableRollout(torch.autograd.Function):
     def backward(ctx, gtraj):
         xd, Ud = ctx.saved_tensors
         named = [(k, p) for k, p in ctx.module.named_parameters()]
+        if any(k == "M_net.L_tril" and p.requires_grad for k, p in named):
+            # the reference keeps the constant mass matrix in the autograd graph (src/mass_matrix.py:130-147); this path has
+            # no cotangent for it, and a silently missing gradient would be worse than an error
+            raise NotImplementedError("training mode: no gradient for M_net.L_tril (constant mass matrix); freeze it "
+                                      "(requires_grad_(False)) or train it with the reference")
         want = {k: tuple(p.shape) for k, p in named if p.requires_grad and (k in _SLOTS.values() or k == "R_diag_raw")}
         dx0, dU, gr = rollout_vjp(ctx.pk, xd, Ud, gtraj.to(ctx.pk.device, torch.float32).contiguous(), ctx.dt, ctx.integrator, want)
         grads = []

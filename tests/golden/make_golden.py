@@ -268,6 +268,51 @@ def gen_canonical():
 
 
 
+def gen_canonical_constM():
+    """Canonical pHNN with the CONSTANT mass matrix of MassMatrixNetwork (src/mass_matrix.py:15-216, mass_type
+    'constant': M = L L^T, exact inverse, no dependence on q), built by the reference's own constructor branch
+    (src/pHNN_canonical.py:79-86) from the cart-pole YAML with ``mass_matrix.type: constant``: forward, autograd VJP,
+    cost + dJ/dU and Adam trajectories of the composition oracle."""
+    import tempfile
+    cfgd = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    cfgd["model"]["mass_matrix"] = {"type": "constant", "init_scale": 1.0}
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
+        yaml.safe_dump(cfgd, f)
+        path = f.name
+    torch.manual_seed(0)
+    model = pHNN_Canonical(path)
+    os.unlink(path)
+    model.eval()
+    with torch.no_grad():   # a non-trivial, non-diagonal factor (the upper triangle is ignored by the reference: tril)
+        model.M_net.L_tril.copy_(torch.tensor([[0.9, 0.7], [0.35, 0.4]]))
+        model.R_diag_raw.copy_(torch.tensor([0.1, -0.3, 0.5, 1.2]))
+    cfg = yaml.safe_load(open(os.path.join(CFG, "pole_stabilization.yaml")))
+    mpc = cfg["mpc"]
+    out = sd_np(model)
+    g = torch.Generator().manual_seed(5)
+    x, u, v = cartpole_points(g, 32)
+    dx, H, gx, gu = fwd_and_vjp(model, x, u, v)
+    out.update(rand_x=x.numpy(), rand_u=u.numpy(), rand_v=v.numpy(), rand_dx=dx.numpy(), rand_H=H.numpy(),
+               rand_gx=gx.numpy(), rand_gu=gu.numpy(), M=model.M_net(x[:1, :2])[0].detach().numpy())
+    Q = torch.diag(torch.tensor(mpc["Q_diag"]))
+    R = torch.diag(torch.tensor(mpc["R_diag"]))
+    xt = torch.tensor(mpc["x_target"])
+    dt = cfg["cartpole"]["dt"]
+    B, Hh, iters = 8, 10, 6
+    x0 = torch.tensor([0.0, 0.05, 0.0, 0.0]) + (torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])
+    U0 = (torch.rand(B, Hh, 1, generator=g) * 2 - 1) * 35.0
+    out.update(mpc_x0=x0.numpy(), mpc_U0=U0.numpy(), mpc_Q=Q.numpy(), mpc_R=R.numpy(), mpc_xt=xt.numpy(),
+               mpc_bounds=np.array([mpc["u_min"], mpc["u_max"]], np.float32), mpc_lr=np.float32(mpc["learning_rate"]),
+               mpc_dt=np.float32(dt))
+    for integ in ("euler", "rk4"):
+        res = composition_solve(model, x0, U0, dt, integ, Q, R, xt, mpc["u_min"], mpc["u_max"], mpc["learning_rate"],
+                                iters, "best")
+        for k, val in res.items():
+            out["mpc_%s_%s" % (integ, k)] = val
+    np.savez(os.path.join(HERE, "canonical_constM.npz"), **out)
+    print("canonical_constM done; M =", out["M"].tolist(), "dx[0] =", out["rand_dx"][0])
+
+
 def gen_closed_loop():
     """Closed loop of the reference pieces: CartPoleSimulator <-> controller, the
     loop body of scripts/run_cartpole_mpc.py:121-176 and scripts/run_mpc_canonical.py:55-95 (warm start)."""
@@ -477,7 +522,7 @@ def gen_train():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train"]
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train", "canonical_constM"]
     if "pendulum" in which:
         gen_pendulum()
     if "h128" in which:
@@ -492,5 +537,7 @@ if __name__ == "__main__":
         gen_cfg4_shape()
     if "cfg5_shape" in which:
         gen_cfg5_shape()
+    if "canonical_constM" in which:
+        gen_canonical_constM()
     if "train" in which:
         gen_train()

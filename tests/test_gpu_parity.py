@@ -16,7 +16,10 @@ from conftest import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
-KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical"}
+# canonical_constM: the canonical pHNN with MassMatrixNetwork(mass_type='constant') (src/mass_matrix.py:15-216), built by the
+# reference's own constructor branch (src/pHNN_canonical.py:79-86)
+KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical",
+         "canonical_constM": "canonical"}
 STEP_TOL = 1e-5
 HORIZON_TOL = 1e-4
 
@@ -250,7 +253,7 @@ def tc_env(env):
     return ops, get_tc
 
 
-@pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256", "canonical"])
+@pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256", "canonical", "canonical_constM"])
 @pytest.mark.parametrize("mode", [4, 3, 2, 1, 5])
 def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
     # modes 4 (3 x FP16 hi/lo), 3 (3xTF32) and 2 (TF32 + BF16 correction product) are held to the FP32 tolerances; mode 1
@@ -339,7 +342,7 @@ def test_tc_matches_fp32_kernel_and_oracle_cfg4_shape(tc_env, env):
 # ---------------------------------------------------------------------------------------------
 # latency kernel (one CTA per instance; the default route for B <= 2 x SM count, hidden <= 128)
 # ---------------------------------------------------------------------------------------------
-LAT_MODELS = ["pendulum", "cartpole_h128", "canonical"]
+LAT_MODELS = ["pendulum", "cartpole_h128", "canonical", "canonical_constM"]
 
 
 @pytest.fixture(scope="module")

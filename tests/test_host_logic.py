@@ -79,6 +79,36 @@ def test_dropin_init_matches_reference_seeding():
     assert p.G_net is not None and not hasattr(p, "G_fixed")
 
 
+def test_dropin_constant_mass_matrix(tmp_path):
+    """mass_matrix.type 'constant' (MassMatrixNetwork, src/pHNN_canonical.py:79-86, src/mass_matrix.py:15-216): the drop-in
+    builds the same module tree (state_dict keys of the fixture recorded from the reference), loads the reference's
+    state_dict, and its (a, b, c) are the reference's M = L L^T; the configuration-dependent types raise."""
+    import yaml
+    from phnn_mpc_b200.dropin.pHNN_canonical import pHNN_Canonical
+    from phnn_mpc_b200.packing import constant_mass_abc
+    cfg = yaml.safe_load(open(os.path.join(CONFIGS, "cartpole_phnn.yaml")))
+    cfg["model"]["mass_matrix"] = {"type": "constant", "init_scale": 1.0}
+    path = tmp_path / "constM.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    torch.manual_seed(0)
+    c = pHNN_Canonical(str(path))
+    z, sd = load_golden("canonical_constM")
+    assert sorted(c.state_dict()) == sorted(sd)
+    for k in ("H_net.net.0.weight", "H_net.net.2.weight", "H_net.net.4.bias", "J", "G"):   # same RNG order as the reference
+        assert np.array_equal(c.state_dict()[k].numpy(), sd[k]), k
+    c.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    a, b, cc = constant_mass_abc(sd["M_net.L_tril"])
+    np.testing.assert_allclose([[a, b], [b, cc]], z["M"], rtol=1e-6)
+    q = torch.zeros(3, 2)
+    np.testing.assert_allclose(c.M_net(q)[0].detach().numpy(), z["M"], rtol=1e-6)
+    np.testing.assert_allclose((c.M_net(q)[1] @ c.M_net.inverse(q)[1]).detach().numpy(), np.eye(2), atol=1e-5)
+    for t in ("diagonal", "full"):
+        cfg["model"]["mass_matrix"] = {"type": t}
+        path.write_text(yaml.safe_dump(cfg))
+        with pytest.raises(NotImplementedError):
+            pHNN_Canonical(str(path))
+
+
 def test_dropin_surface_matches_reference_signatures():
     import inspect
     from phnn_mpc_b200.dropin import integrators, mpc_controller, mpc_controller_canonical

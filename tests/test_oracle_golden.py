@@ -11,7 +11,10 @@ from conftest import load_golden, rel_err
 from oracle.phnn_oracle import OracleModel
 
 TOL = 2e-5
-KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical"}
+# canonical_constM: the canonical pHNN with MassMatrixNetwork(mass_type='constant') (src/mass_matrix.py:15-216), built by the
+# reference's own constructor branch (src/pHNN_canonical.py:79-86)
+KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical",
+         "canonical_constM": "canonical"}
 
 
 @pytest.mark.parametrize("name", list(KINDS))
