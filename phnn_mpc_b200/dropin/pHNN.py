@@ -28,6 +28,9 @@ def _flatten_rows(t):
 def run_forward_op(module, x, u):
     """Stage (x, u) to the module's CUDA pack, run the op, return results on x's device."""
     x2, u2 = _flatten_rows(x), _flatten_rows(u)
+    for net in (getattr(module, "H_net", None), getattr(module, "R_net", None), getattr(module, "G_net", None)):
+        if net is not None and hasattr(net, "check_mode"):
+            net.check_mode()
     if not torch.cuda.is_available():
         raise RuntimeError("phnn_mpc_b200 has no CPU fallback: a CUDA device is required for forward()")
     pk = pack_of(module)
@@ -54,7 +57,7 @@ class pHNN(nn.Module):
             self.G_net = _mlp_from_config(model_cfg["G_mlp"], n, m * n)
         nets = [self.R_net, self.H_net] + ([self.G_net] if self.G_net is not None else [])
         if not all(net.kernel_compatible() for net in nets):
-            raise NotImplementedError("CUDA kernels cover Tanh MLPs with bias and without LayerNorm/Dropout "
+            raise NotImplementedError("CUDA kernels cover Tanh MLPs with bias and without LayerNorm "
                                       "(all shipped configs); got another variant")
 
     def forward(self, x, u):

@@ -24,6 +24,33 @@ def infer_kind(sd):
     return "canonical" if "R_diag_raw" in sd else "phnn"
 
 
+def normalize_state_dict(sd):
+    """Reference MLPs built with ``dropout > 0`` (src/NN.py:16-25) interleave ``nn.Dropout`` modules, which shifts the
+    Sequential indices of the Linear layers (``net.0, net.3, net.6`` instead of ``net.0, net.2, net.4``).  Dropout is the
+    identity in eval mode -- the mode both controllers put the model in (src/mpc_controller.py:44,
+    src/mpc_controller_canonical.py:54) -- so such a checkpoint is the same function: rename the k-th Linear of every net
+    to ``net.<2k>``.  A LayerNorm (1-D ``weight`` under ``net.<i>``) is not the identity and raises."""
+    out = dict(sd)
+    for prefix in ("H_net", "R_net", "G_net"):
+        idx = sorted({int(k.split(".")[2]) for k in sd if k.startswith(prefix + ".net.") and k.endswith(".weight")})
+        if not idx:
+            continue
+        for i in idx:
+            w = sd["%s.net.%d.weight" % (prefix, i)]
+            if len(tuple(w.shape)) != 2:
+                raise NotImplementedError("%s.net.%d is not a Linear layer (LayerNorm?): not built for the CUDA path" % (prefix, i))
+        if idx == [2 * j for j in range(len(idx))]:
+            continue
+        for k in [k for k in out if k.startswith(prefix + ".net.")]:
+            del out[k]
+        for j, i in enumerate(idx):
+            for leaf in ("weight", "bias"):
+                src = "%s.net.%d.%s" % (prefix, i, leaf)
+                if src in sd:
+                    out["%s.net.%d.%s" % (prefix, 2 * j, leaf)] = sd[src]
+    return out
+
+
 def constant_mass_abc(L_tril):
     """(a, b, c) of the constant mass matrix M = L L^T = [[a, b], [b, c]] of MassMatrixNetwork(mass_type='constant')
     (src/mass_matrix.py:130-147): L = tril(L_tril) with softplus(diag) + 1e-3 on the diagonal, float32 arithmetic."""
@@ -46,7 +73,7 @@ class PackedModel:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("phnn_mpc_b200 runs on CUDA devices only, got %s" % self.device)
-        sd = dict(state_dict)
+        sd = normalize_state_dict(dict(state_dict))
         kind = kind or infer_kind(sd)
         keep = []
 

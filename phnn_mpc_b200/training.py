@@ -100,5 +100,10 @@ def trainable_rollout(model, y0, controls, dt, integrator="euler"):
     y0 = y0 if y0.ndim == 2 else y0.reshape(1, -1)
     if integrator not in ops.INTEGRATORS:
         raise ValueError(f"Unknown integrator: {integrator}")
+    for net in (getattr(model, "H_net", None), getattr(model, "R_net", None), getattr(model, "G_net", None)):
+        if net is not None and getattr(net, "dropout_p", 0.0) > 0.0:
+            # the gradient slots are keyed by the dropout-free layer indices, and a training-mode forward would need the
+            # reference's random masks: neither exists on this path
+            raise NotImplementedError("training mode is built for MLPs without Dropout")
     params = [p for _, p in model.named_parameters()]
     return _TrainableRollout.apply(model, float(dt), integrator, y0, controls.reshape(y0.shape[0], -1, controls.shape[-1]), *params)

@@ -38,7 +38,8 @@ def load_reference_checkpoint(path):
 
 
 def describe(state_dict):
-    sd = state_dict
+    from .packing import normalize_state_dict
+    sd = normalize_state_dict(state_dict)
     kind = 1 if "R_diag_raw" in sd else 0
     W1 = _to_np(sd["H_net.net.0.weight"])
     h, n = int(W1.shape[0]), int(W1.shape[1])

@@ -217,6 +217,50 @@ def gen_cartpole(hidden, seed, name):
     print(name, "done; H[0..2] =", out["rand_H"][:3])
 
 
+def gen_cartpole_dropout():
+    """Cart-pole pHNN whose MLPs were built with dropout = 0.1 (src/NN.py:16-25: nn.Dropout after every activation, so the
+    Linear layers sit at net.0 / net.3 / net.6), in EVAL mode -- the mode MPCController puts the model in
+    (src/mpc_controller.py:44): forward, autograd VJP and the composition oracle, plus the real controller on one state."""
+    cfgd = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    cfgd["model"]["H_mlp"]["dropout"] = 0.1
+    cfgd["model"]["R_mlp"]["dropout"] = 0.1
+    f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+    yaml.safe_dump(cfgd, f)
+    f.close()
+    torch.manual_seed(21)
+    model = pHNN(f.name)
+    os.unlink(f.name)
+    model.eval()
+    mpc = cfgd["mpc"]
+    out = sd_np(model)
+    g = torch.Generator().manual_seed(9)
+    x, u, v = cartpole_points(g, 32)
+    dx, H, gx, gu = fwd_and_vjp(model, x, u, v)
+    out.update(rand_x=x.numpy(), rand_u=u.numpy(), rand_v=v.numpy(), rand_dx=dx.numpy(), rand_H=H.numpy(),
+               rand_gx=gx.numpy(), rand_gu=gu.numpy())
+    Q = torch.diag(torch.tensor(mpc["Q_diag"]))
+    R = torch.tensor([[mpc["R_diag"][0]]])
+    xt = torch.tensor(mpc["x_target"])
+    dt = cfgd["cartpole"]["dt"]
+    B, Hh, iters = 8, 12, 5
+    x0 = x[:B]
+    U0 = (torch.rand(B, Hh, 1, generator=g) * 2 - 1) * 18.0
+    out.update(mpc_x0=x0.numpy(), mpc_U0=U0.numpy(), mpc_Q=Q.numpy(), mpc_R=R.numpy(), mpc_xt=xt.numpy(),
+               mpc_bounds=np.array([mpc["u_min"], mpc["u_max"]], np.float32), mpc_lr=np.float32(mpc["learning_rate"]),
+               mpc_dt=np.float32(dt))
+    for integ in ("euler", "rk4"):
+        res = composition_solve(model, x0, U0, dt, integ, Q, R, xt, mpc["u_min"], mpc["u_max"], mpc["learning_rate"],
+                                iters, "last")
+        for k, val in res.items():
+            out["mpc_%s_%s" % (integ, k)] = val
+    ctrl = MPCController(model, mpc["horizon"], dt, mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"], mpc["u_min"],
+                         mpc["u_max"], optimizer_type="Adam", lr=mpc["learning_rate"], max_iterations=mpc["optimizer_steps"])
+    xs = np.array([[0.0, 0.1, 0.0, 0.0]], np.float64)
+    out.update(ctrl_x=xs, ctrl_u=np.stack([ctrl.compute_control(s) for s in xs]))
+    np.savez(os.path.join(HERE, "cartpole_h128_dropout.npz"), **out)
+    print("cartpole_h128_dropout done; keys:", sorted(k for k in out if k.startswith("sd/H_net")))
+
+
 def gen_canonical():
     torch.manual_seed(0)
     model = pHNN_Canonical(os.path.join(CFG, "cartpole_phnn.yaml"))
@@ -522,7 +566,7 @@ def gen_train():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train", "canonical_constM"]
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train", "canonical_constM", "dropout"]
     if "pendulum" in which:
         gen_pendulum()
     if "h128" in which:
@@ -539,5 +583,7 @@ if __name__ == "__main__":
         gen_cfg5_shape()
     if "canonical_constM" in which:
         gen_canonical_constM()
+    if "dropout" in which:
+        gen_cartpole_dropout()
     if "train" in which:
         gen_train()

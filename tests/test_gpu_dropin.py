@@ -89,6 +89,31 @@ def test_integrators_dropin_pendulum():
         I.rollout_trajectory(m, x, U10, 0.05, "midpoint")
 
 
+def test_dropout_model_through_dropin_controller(tmp_path):
+    """a model whose MLPs carry Dropout (src/NN.py:16-25): the controller puts it in eval mode (src/mpc_controller.py:44), where
+    Dropout is the identity; forward and compute_control against the values recorded from the reference in eval mode"""
+    from phnn_mpc_b200.dropin.pHNN import pHNN
+    from phnn_mpc_b200.dropin.mpc_controller import MPCController
+    cfg = yaml.safe_load(open(os.path.join(CONFIGS, "cartpole_phnn.yaml")))
+    cfg["model"]["H_mlp"]["dropout"] = 0.1
+    cfg["model"]["R_mlp"]["dropout"] = 0.1
+    path = tmp_path / "dropout.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    z, sd = load_golden("cartpole_h128_dropout")
+    m = pHNN(str(path))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    with pytest.raises(RuntimeError, match="eval"):            # a fresh module is in training mode
+        m(torch.from_numpy(z["rand_x"]), torch.from_numpy(z["rand_u"]))
+    mpc = cfg["mpc"]
+    c = MPCController(m, mpc["horizon"], 0.02, mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"], mpc["u_min"],
+                      mpc["u_max"], optimizer_type="Adam", lr=mpc["learning_rate"], max_iterations=mpc["optimizer_steps"])
+    assert not m.training
+    dx, H = m(torch.from_numpy(z["rand_x"]), torch.from_numpy(z["rand_u"]))
+    assert rel_err(dx.numpy(), z["rand_dx"]) < 1e-5 and rel_err(H.numpy(), z["rand_H"]) < 1e-5
+    u = c.compute_control(z["ctrl_x"][0])
+    assert abs(u[0] - z["ctrl_u"][0][0]) < 0.02 * mpc["learning_rate"]
+
+
 def test_mpc_controller_compute_control_cfg1():
     """BASELINE config 1: MPCController.compute_control, B=1, YAML parameters."""
     from phnn_mpc_b200.dropin.mpc_controller import MPCController

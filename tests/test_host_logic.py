@@ -109,6 +109,35 @@ def test_dropin_constant_mass_matrix(tmp_path):
             pHNN_Canonical(str(path))
 
 
+def test_dropin_dropout_mlps_eval_mode(tmp_path):
+    """MLPs configured with dropout > 0 (src/NN.py:16-25): the drop-in builds the reference's module tree (Linear layers at
+    net.0 / net.3 / net.6, same RNG order), loads its state_dict, maps the keys to the dropout-free layout for the kernels
+    and refuses a forward in training mode (Dropout is the identity only in eval mode, src/mpc_controller.py:44)."""
+    import yaml
+    from phnn_mpc_b200.dropin.pHNN import pHNN
+    from phnn_mpc_b200.packing import normalize_state_dict
+    cfg = yaml.safe_load(open(os.path.join(CONFIGS, "cartpole_phnn.yaml")))
+    cfg["model"]["H_mlp"]["dropout"] = 0.1
+    cfg["model"]["R_mlp"]["dropout"] = 0.1
+    path = tmp_path / "dropout.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    torch.manual_seed(21)
+    m = pHNN(str(path))
+    z, sd = load_golden("cartpole_h128_dropout")
+    assert sorted(m.state_dict()) == sorted(sd)
+    for k, v in sd.items():
+        assert np.array_equal(m.state_dict()[k].numpy(), v), k
+    nsd = normalize_state_dict(sd)
+    assert "H_net.net.4.weight" in nsd and "H_net.net.6.weight" not in nsd and "R_net.net.2.bias" in nsd
+    assert np.array_equal(nsd["H_net.net.2.weight"], sd["H_net.net.3.weight"])
+    assert normalize_state_dict(load_golden("cartpole_h128")[1]).keys() == load_golden("cartpole_h128")[1].keys()
+    m.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        m(torch.zeros(1, 4), torch.zeros(1, 1))
+    with pytest.raises(NotImplementedError):
+        normalize_state_dict({"H_net.net.0.weight": np.zeros((8, 4)), "H_net.net.1.weight": np.zeros(8)})   # LayerNorm
+
+
 def test_dropin_surface_matches_reference_signatures():
     import inspect
     from phnn_mpc_b200.dropin import integrators, mpc_controller, mpc_controller_canonical

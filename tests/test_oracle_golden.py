@@ -13,8 +13,9 @@ from oracle.phnn_oracle import OracleModel
 TOL = 2e-5
 # canonical_constM: the canonical pHNN with MassMatrixNetwork(mass_type='constant') (src/mass_matrix.py:15-216), built by the
 # reference's own constructor branch (src/pHNN_canonical.py:79-86)
+# cartpole_h128_dropout: MLPs built with dropout = 0.1 (Linear layers at net.0 / net.3 / net.6), recorded in eval mode
 KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical",
-         "canonical_constM": "canonical"}
+         "canonical_constM": "canonical", "cartpole_h128_dropout": "phnn"}
 
 
 @pytest.mark.parametrize("name", list(KINDS))
