@@ -33,11 +33,11 @@ class MLP(nn.Module):
                 nn.init.uniform_(lin.bias, -bound, bound)
 
     def kernel_compatible(self):
-        """True when the CUDA kernels implement this stack: Tanh, bias, no LayerNorm.  Dropout layers are accepted: they are
-        the identity in eval mode, which is the mode the controllers put the model in (src/mpc_controller.py:44,
-        src/mpc_controller_canonical.py:54); ``check_mode`` refuses a forward in training mode."""
-        lin = [m for m in self.net if isinstance(m, nn.Linear)]
-        return self.activation_name == "Tanh" and not self.uses_layer_norm and all(l.bias is not None for l in lin)
+        """True when the CUDA kernels implement this stack: Tanh, no LayerNorm.  Dropout layers are accepted: they are the
+        identity in eval mode, which is the mode the controllers put the model in (src/mpc_controller.py:44,
+        src/mpc_controller_canonical.py:54); ``check_mode`` refuses a forward in training mode.  ``bias=False`` is a
+        zero bias for the kernels."""
+        return self.activation_name == "Tanh" and not self.uses_layer_norm
 
     def check_mode(self):
         if self.dropout_p > 0.0 and self.training:

@@ -57,7 +57,7 @@ class pHNN(nn.Module):
             self.G_net = _mlp_from_config(model_cfg["G_mlp"], n, m * n)
         nets = [self.R_net, self.H_net] + ([self.G_net] if self.G_net is not None else [])
         if not all(net.kernel_compatible() for net in nets):
-            raise NotImplementedError("CUDA kernels cover Tanh MLPs with bias and without LayerNorm "
+            raise NotImplementedError("CUDA kernels cover Tanh MLPs without LayerNorm "
                                       "(all shipped configs); got another variant")
 
     def forward(self, x, u):

@@ -38,7 +38,7 @@ class pHNN_Canonical(nn.Module):
                                            init_scale=mm.get("init_scale", 1.0))
         self.H_net = _mlp_from_config(model_cfg["H_mlp"], self.state_dim, 1)
         if not self.H_net.kernel_compatible():
-            raise NotImplementedError("CUDA kernels cover Tanh MLPs with bias and without LayerNorm")
+            raise NotImplementedError("CUDA kernels cover Tanh MLPs without LayerNorm")
         qd = self.q_dim
         J = torch.zeros(2 * qd, 2 * qd)
         J[:qd, qd:] = torch.eye(qd)

@@ -39,15 +39,18 @@ def normalize_state_dict(sd):
             w = sd["%s.net.%d.weight" % (prefix, i)]
             if len(tuple(w.shape)) != 2:
                 raise NotImplementedError("%s.net.%d is not a Linear layer (LayerNorm?): not built for the CUDA path" % (prefix, i))
-        if idx == [2 * j for j in range(len(idx))]:
-            continue
-        for k in [k for k in out if k.startswith(prefix + ".net.")]:
-            del out[k]
-        for j, i in enumerate(idx):
-            for leaf in ("weight", "bias"):
-                src = "%s.net.%d.%s" % (prefix, i, leaf)
-                if src in sd:
-                    out["%s.net.%d.%s" % (prefix, 2 * j, leaf)] = sd[src]
+        if idx != [2 * j for j in range(len(idx))]:
+            for k in [k for k in out if k.startswith(prefix + ".net.")]:
+                del out[k]
+            for j, i in enumerate(idx):
+                for leaf in ("weight", "bias"):
+                    src = "%s.net.%d.%s" % (prefix, i, leaf)
+                    if src in sd:
+                        out["%s.net.%d.%s" % (prefix, 2 * j, leaf)] = sd[src]
+        # ``bias: false`` (src/NN.py:19,25): a Linear without bias is the same function as one with a zero bias
+        for j in range(len(idx)):
+            if "%s.net.%d.bias" % (prefix, 2 * j) not in out:
+                out["%s.net.%d.bias" % (prefix, 2 * j)] = np.zeros(int(out["%s.net.%d.weight" % (prefix, 2 * j)].shape[0]), np.float32)
     return out
 
 

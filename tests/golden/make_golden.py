@@ -261,6 +261,49 @@ def gen_cartpole_dropout():
     print("cartpole_h128_dropout done; keys:", sorted(k for k in out if k.startswith("sd/H_net")))
 
 
+def gen_canonical_nobias():
+    """Canonical pHNN whose H_mlp is configured with ``bias: false`` (src/NN.py:19,25: Linear layers without bias), by the
+    reference's constructor: forward, autograd VJP and the composition oracle."""
+    cfgd = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))
+    cfgd["model"]["H_mlp"]["bias"] = False
+    f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+    yaml.safe_dump(cfgd, f)
+    f.close()
+    torch.manual_seed(33)
+    model = pHNN_Canonical(f.name)
+    os.unlink(f.name)
+    model.eval()
+    with torch.no_grad():
+        model.M_net.log_a.copy_(torch.tensor(0.1))
+        model.M_net.b.copy_(torch.tensor(0.25))
+        model.R_diag_raw.copy_(torch.tensor([0.2, -0.1, 0.4, 0.9]))
+    cfg = yaml.safe_load(open(os.path.join(CFG, "pole_stabilization.yaml")))
+    mpc = cfg["mpc"]
+    out = sd_np(model)
+    g = torch.Generator().manual_seed(13)
+    x, u, v = cartpole_points(g, 32)
+    dx, H, gx, gu = fwd_and_vjp(model, x, u, v)
+    out.update(rand_x=x.numpy(), rand_u=u.numpy(), rand_v=v.numpy(), rand_dx=dx.numpy(), rand_H=H.numpy(),
+               rand_gx=gx.numpy(), rand_gu=gu.numpy())
+    Q = torch.diag(torch.tensor(mpc["Q_diag"]))
+    R = torch.diag(torch.tensor(mpc["R_diag"]))
+    xt = torch.tensor(mpc["x_target"])
+    dt = cfg["cartpole"]["dt"]
+    B, Hh, iters = 8, 10, 6
+    x0 = torch.tensor([0.0, 0.05, 0.0, 0.0]) + (torch.rand(B, 4, generator=g) * 2 - 1) * torch.tensor([1.0, 0.3, 0.5, 0.5])
+    U0 = (torch.rand(B, Hh, 1, generator=g) * 2 - 1) * 35.0
+    out.update(mpc_x0=x0.numpy(), mpc_U0=U0.numpy(), mpc_Q=Q.numpy(), mpc_R=R.numpy(), mpc_xt=xt.numpy(),
+               mpc_bounds=np.array([mpc["u_min"], mpc["u_max"]], np.float32), mpc_lr=np.float32(mpc["learning_rate"]),
+               mpc_dt=np.float32(dt))
+    for integ in ("euler", "rk4"):
+        res = composition_solve(model, x0, U0, dt, integ, Q, R, xt, mpc["u_min"], mpc["u_max"], mpc["learning_rate"],
+                                iters, "best")
+        for k, val in res.items():
+            out["mpc_%s_%s" % (integ, k)] = val
+    np.savez(os.path.join(HERE, "canonical_nobias.npz"), **out)
+    print("canonical_nobias done; keys:", sorted(k for k in out if k.startswith("sd/H_net")))
+
+
 def gen_canonical():
     torch.manual_seed(0)
     model = pHNN_Canonical(os.path.join(CFG, "cartpole_phnn.yaml"))
@@ -566,7 +609,7 @@ def gen_train():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train", "canonical_constM", "dropout"]
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train", "canonical_constM", "dropout", "nobias"]
     if "pendulum" in which:
         gen_pendulum()
     if "h128" in which:
@@ -585,5 +628,7 @@ if __name__ == "__main__":
         gen_canonical_constM()
     if "dropout" in which:
         gen_cartpole_dropout()
+    if "nobias" in which:
+        gen_canonical_nobias()
     if "train" in which:
         gen_train()

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 # reference's own constructor branch (src/pHNN_canonical.py:79-86)
 # cartpole_h128_dropout: MLPs built with dropout = 0.1 (Linear layers at net.0 / net.3 / net.6), recorded in eval mode
 KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical",
-         "canonical_constM": "canonical", "cartpole_h128_dropout": "phnn"}
+         "canonical_constM": "canonical", "cartpole_h128_dropout": "phnn", "canonical_nobias": "canonical"}   # nobias: H_mlp bias: false
 STEP_TOL = 1e-5
 HORIZON_TOL = 1e-4
 
@@ -254,7 +254,7 @@ def tc_env(env):
     return ops, get_tc
 
 
-@pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256", "canonical", "canonical_constM", "cartpole_h128_dropout"])
+@pytest.mark.parametrize("name", ["cartpole_h128", "cartpole_h256", "canonical", "canonical_constM", "cartpole_h128_dropout", "canonical_nobias"])
 @pytest.mark.parametrize("mode", [4, 3, 2, 1, 5])
 def test_tc_forward_rollout_costgrad_solve_golden(tc_env, name, mode):
     # modes 4 (3 x FP16 hi/lo), 3 (3xTF32) and 2 (TF32 + BF16 correction product) are held to the FP32 tolerances; mode 1
@@ -343,7 +343,7 @@ def test_tc_matches_fp32_kernel_and_oracle_cfg4_shape(tc_env, env):
 # ---------------------------------------------------------------------------------------------
 # latency kernel (one CTA per instance; the default route for B <= 2 x SM count, hidden <= 128)
 # ---------------------------------------------------------------------------------------------
-LAT_MODELS = ["pendulum", "cartpole_h128", "canonical", "canonical_constM", "cartpole_h128_dropout"]
+LAT_MODELS = ["pendulum", "cartpole_h128", "canonical", "canonical_constM", "cartpole_h128_dropout", "canonical_nobias"]
 
 
 @pytest.fixture(scope="module")

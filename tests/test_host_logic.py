@@ -136,6 +136,18 @@ def test_dropin_dropout_mlps_eval_mode(tmp_path):
         m(torch.zeros(1, 4), torch.zeros(1, 1))
     with pytest.raises(NotImplementedError):
         normalize_state_dict({"H_net.net.0.weight": np.zeros((8, 4)), "H_net.net.1.weight": np.zeros(8)})   # LayerNorm
+    # bias: false (src/NN.py:19,25): same module tree as the reference, zero biases for the kernels
+    from phnn_mpc_b200.dropin.pHNN_canonical import pHNN_Canonical
+    cfg = yaml.safe_load(open(os.path.join(CONFIGS, "cartpole_phnn.yaml")))
+    cfg["model"]["H_mlp"]["bias"] = False
+    path.write_text(yaml.safe_dump(cfg))
+    torch.manual_seed(33)
+    c = pHNN_Canonical(str(path))
+    _, sdn = load_golden("canonical_nobias")
+    assert sorted(c.state_dict()) == sorted(sdn) and "H_net.net.0.bias" not in sdn
+    assert np.array_equal(c.state_dict()["H_net.net.2.weight"].numpy(), sdn["H_net.net.2.weight"])
+    nb = normalize_state_dict(sdn)
+    assert all(np.all(nb["H_net.net.%d.bias" % i] == 0) for i in (0, 2, 4)) and nb["H_net.net.4.bias"].shape == (1,)
 
 
 def test_dropin_surface_matches_reference_signatures():

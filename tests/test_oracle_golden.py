@@ -15,7 +15,7 @@ TOL = 2e-5
 # reference's own constructor branch (src/pHNN_canonical.py:79-86)
 # cartpole_h128_dropout: MLPs built with dropout = 0.1 (Linear layers at net.0 / net.3 / net.6), recorded in eval mode
 KINDS = {"pendulum": "phnn", "cartpole_h128": "phnn", "cartpole_h256": "phnn", "canonical": "canonical",
-         "canonical_constM": "canonical", "cartpole_h128_dropout": "phnn"}
+         "canonical_constM": "canonical", "cartpole_h128_dropout": "phnn", "canonical_nobias": "canonical"}   # nobias: H_mlp bias: false
 
 
 @pytest.mark.parametrize("name", list(KINDS))
