@@ -54,13 +54,37 @@ class MPCController:
         if self.optimizer_type == "Adam":
             return
         if self.optimizer_type == "LBFGS":
-            raise NotImplementedError("the LBFGS branch of the reference (src/mpc_controller.py:169-170) is not "
-                                      "implemented: no driver selects it; use optimizer_type='Adam'")
+            return
         raise ValueError(f"Unknown optimizer type: {self.optimizer_type}")
+
+    def _compute_control_lbfgs(self, current_state, return_sequence=False):
+        """src/mpc_controller.py:169-170,174-199: ``torch.optim.LBFGS(lr, max_iter=20)`` stepped ``max_iterations`` times.  The
+        optimiser is torch's own (its two-loop recursion and stopping rules are the algorithm); its closure -- clamp, Euler
+        rollout, cost, backward -- is one launch of the fused cost + adjoint kernel per evaluation."""
+        eng = self._engine()
+        x0 = current_state.reshape(1, -1)
+        control_sequence = torch.zeros(self.horizon, 1, requires_grad=True)
+        optimizer = torch.optim.LBFGS([control_sequence], lr=self.lr, max_iter=20)
+
+        def closure():
+            optimizer.zero_grad()
+            cost, g, _ = eng.cost_and_grad(x0, control_sequence.detach().reshape(1, self.horizon, 1))
+            control_sequence.grad = g[0].to("cpu", torch.float32).reshape(self.horizon, 1)
+            return cost[0].to("cpu")
+
+        for _ in range(self.max_iterations):
+            optimizer.step(closure)
+        with torch.no_grad():
+            seq = control_sequence.detach()
+            if self.u_min is not None and self.u_max is not None:
+                seq = torch.clamp(seq, self.u_min, self.u_max)
+        return seq.numpy() if return_sequence else seq[0].numpy()
 
     def solve_batch(self, states, U0=None, integrator="euler", want_hist=False):
         """B independent solves in one launch.  states [B,n] -> dict(U, u0, best_cost, cost_hist)."""
         self._check_optimizer()
+        if self.optimizer_type != "Adam":
+            raise NotImplementedError("solve_batch runs the fused Adam solve; the LBFGS branch is per instance (compute_control)")
         return self._engine(integrator).solve(states, U0, want_hist)
 
     def compute_control(self, current_state):
@@ -68,6 +92,8 @@ class MPCController:
         self._check_optimizer()
         if isinstance(current_state, np.ndarray):
             current_state = torch.tensor(current_state, dtype=torch.float32)
+        if self.optimizer_type == "LBFGS":
+            return self._compute_control_lbfgs(current_state)
         out = self._engine().solve(current_state.reshape(1, -1))
         return out["u0"][0].cpu().numpy()
 

@@ -304,6 +304,46 @@ def gen_canonical_nobias():
     print("canonical_nobias done; keys:", sorted(k for k in out if k.startswith("sd/H_net")))
 
 
+def gen_lbfgs():
+    """The LBFGS branch of MPCController.compute_control (src/mpc_controller.py:169-170: torch.optim.LBFGS(lr, max_iter=20),
+    stepped max_iterations times) on the cartpole_h128 model: three states, a short configuration (H=10, 3 outer steps)."""
+    z = np.load(os.path.join(HERE, "cartpole_h128.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model = pHNN(os.path.join(CFG, "cartpole_phnn.yaml"))
+    model.load_state_dict(sd)
+    model.eval()
+    mpc = yaml.safe_load(open(os.path.join(CFG, "cartpole_phnn.yaml")))["mpc"]
+    xs = np.array([[0.0, 0.1, 0.0, 0.0], [0.3, -0.12, 0.2, -0.4], [-0.5, 0.2, -0.3, 0.6]], np.float64)
+    out = {"x": xs}
+    for lr, tag in ((0.05, "a"), (0.2, "b")):
+        ctrl = MPCController(model, 10, 0.02, mpc["Q_diag"], mpc["R_diag"][0], mpc["x_target"], mpc["u_min"], mpc["u_max"],
+                             optimizer_type="LBFGS", lr=lr, max_iterations=3)
+        out["u_" + tag] = np.stack([ctrl.compute_control(s) for s in xs])
+        out["lr_" + tag] = np.float32(lr)
+        # the cost the branch reaches: the same loop again with the controller's own rollout_dynamics / compute_cost
+        # (compute_control does not return the sequence); bit-identical to the call above (deterministic CPU arithmetic)
+        Js = []
+        for s_ in xs:
+            x0 = torch.tensor(s_, dtype=torch.float32)
+            cs = torch.zeros(10, 1, requires_grad=True)
+            opt = torch.optim.LBFGS([cs], lr=lr, max_iter=20)
+
+            def closure():
+                opt.zero_grad()
+                c = torch.clamp(cs, mpc["u_min"], mpc["u_max"])
+                J = ctrl.compute_cost(ctrl.rollout_dynamics(x0, c), c)
+                J.backward()
+                return J
+            for _ in range(3):
+                opt.step(closure)
+            c = torch.clamp(cs.detach(), mpc["u_min"], mpc["u_max"])   # (the model needs autograd for grad H: no no_grad here)
+            assert abs(float(c[0]) - float(out["u_" + tag][len(Js)][0])) < 1e-6
+            Js.append(float(ctrl.compute_cost(ctrl.rollout_dynamics(x0, c), c).item()))
+        out["J_" + tag] = np.array(Js, np.float32)
+    np.savez(os.path.join(HERE, "lbfgs.npz"), **out)
+    print("lbfgs done; u =", out["u_a"].ravel(), out["u_b"].ravel())
+
+
 def gen_canonical():
     torch.manual_seed(0)
     model = pHNN_Canonical(os.path.join(CFG, "cartpole_phnn.yaml"))
@@ -609,7 +649,7 @@ def gen_train():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train", "canonical_constM", "dropout", "nobias"]
+    which = sys.argv[1:] or ["pendulum", "h128", "h256", "canonical", "closed_loop", "cfg4_shape", "cfg5_shape", "train", "canonical_constM", "dropout", "nobias", "lbfgs"]
     if "pendulum" in which:
         gen_pendulum()
     if "h128" in which:
@@ -630,5 +670,7 @@ if __name__ == "__main__":
         gen_cartpole_dropout()
     if "nobias" in which:
         gen_canonical_nobias()
+    if "lbfgs" in which:
+        gen_lbfgs()
     if "train" in which:
         gen_train()
